@@ -1,0 +1,859 @@
+// libhpv C ABI (include/hpv.h): context, device memory, launch sequencing.  No arithmetic of the hot path
+// lives here -- that is all in the kernels -- and there is no CPU fallback: without a CUDA device every
+// compute entry point fails with HPV_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/hpv.h"
+#include "hpv_host_prep.h"
+#include "hpv_launch.h"
+
+namespace {
+
+std::string g_create_error;
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(T));
+        if (e == cudaSuccess) n = count ? count : 1; else p = nullptr;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct PointSet {
+    bool active = false;
+    int n = 0, mx = 0, my = 0, n_ctas = 0;
+    float a0[HPV_NFIELDS], a1[HPV_NFIELDS];
+    float weight = 1.0f;
+    DevBuf<float> pts, target, resid, gbar, blk_loss;
+};
+
+}  // namespace
+
+struct hpv_ctx {
+    int device = 0, n_sm = 0;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    std::string err;
+    long long launches = 0;
+
+    HpvNet net; bool have_net = false;
+    int Q = 0; std::vector<double> xi, w; bool have_quad = false;
+    int N = 0; std::vector<double> T, D1, D2, d1b; bool have_tabs = false, have_d1b = false;
+    int problem = -1, var_form = -1; double V = 1.0; HpvForm form; bool have_form = false;
+    int n_el = 0, ntx = 0, nty = 0; bool have_el = false, has_F = false;
+    bool ready = false;
+
+    // parameters / optimiser
+    DevBuf<float> theta_pad, eps;
+    DevBuf<double> master, adam_m, adam_v, grad_out;
+    DevBuf<int> pad_index, step;
+    // quadrature / tables
+    DevBuf<float> xi1, tab[HPV_NTAB];
+    // elements
+    DevBuf<float> geom, F, Res, el_loss, Upart, Gbar;
+    DevBuf<int> ntest, cta_tile_begin, el_first_cta, el_part_off, el_nparts;
+    DevBuf<unsigned int> counters;                 // [n_el] el_done, then n_done
+    DevBuf<double> loss;
+    HpvPartition part;
+    // backward
+    DevBuf<float> grad_part, redbuf;
+    int bwd_block = 0, bwd_grid = 0, bwd_ctas_per_sm = 0, grad_stride = 0, loss_off = 0;
+    size_t bwd_smem = 0, fwd_smem = 0, adj_smem = 0;
+    int fwd_ctas_per_sm = 0, adj_grid = 0, slabs_per_el = 0;
+    PointSet ps[HPV_MAX_POINT_SETS];
+    // training configuration
+    double wv = 1.0; unsigned mask = 0; int train_eps = 0;
+    double lr = 1e-3, b1 = 0.9, b2 = 0.999, eps_hat = 1e-8;
+    std::vector<float> host_f32;
+    std::vector<double> host_f64;
+};
+
+namespace {
+
+int fail(hpv_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define HPV_CK(call)                                                                                 \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return fail(c, HPV_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));       \
+    } while (0)
+
+template <typename T>
+int upload(hpv_ctx* c, DevBuf<T>& b, const std::vector<T>& h) {
+    HPV_CK(b.alloc(h.size()));
+    if (!h.empty()) HPV_CK(cudaMemcpyAsync(b.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    HPV_CK(cudaStreamSynchronize(c->stream));      // the host vector may be a temporary
+    return HPV_OK;
+}
+
+HpvKernelKey key_of(const hpv_ctx* c, int mx, int my) {
+    HpvKernelKey k;
+    k.dim = c->net.dim; k.mx = mx; k.my = my; k.hp = c->net.hp; k.act = c->net.act;
+    hpv_canon_mode(k.dim, k.mx, k.my);
+    return k;
+}
+
+void fill_var_args(hpv_ctx* c, HpvVarArgs& a) {
+    memset(&a, 0, sizeof(a));
+    a.theta_pad = c->theta_pad.p; a.theta_pad_n = c->net.theta_pad_n; a.nhid = c->net.nhid; a.eps = c->eps.p;
+    a.Q = c->Q; a.rows = (c->net.dim == 2) ? c->Q : 1; a.xi1 = c->xi1.p;
+    for (int t = 0; t < HPV_NTAB; ++t) a.tab[t] = c->tab[t].p;
+    a.n_el = c->n_el; a.el_geom = c->geom.p; a.el_ntest = c->ntest.p; a.ntx = c->ntx; a.nty = c->nty;
+    a.F = c->has_F ? c->F.p : nullptr;
+    a.n_terms = c->form.n_terms;
+    for (int t = 0; t < HPV_MAX_TERMS; ++t) a.terms[t] = c->form.terms[t];
+    a.tiles_per_el = c->part.tiles_per_el; a.n_ctas = c->part.n_ctas;
+    a.cta_tile_begin = c->cta_tile_begin.p; a.el_first_cta = c->el_first_cta.p;
+    a.el_part_off = c->el_part_off.p; a.el_nparts = c->el_nparts.p;
+    a.Upart = c->Upart.p; a.el_done = c->counters.p; a.n_done = c->counters.p + c->n_el;
+    a.Res = c->Res.p; a.el_loss = c->el_loss.p; a.loss = c->loss.p;
+    a.grad_part = c->grad_part.p; a.grad_stride = c->grad_stride; a.grad_pad = c->redbuf.p;
+    a.bwd_done = nullptr; a.loss_scale = (float)c->wv;
+}
+
+// Choose the block size of the MLP reverse sweep: the largest number of resident threads per SM that the
+// shared-memory plan (HpvBwdSmem) allows.
+int plan_bwd(hpv_ctx* c, int mx, int my, int& block, int& ctas_per_sm, size_t& smem) {
+    const HpvKernelKey k = key_of(c, mx, my);
+    HpvVarArgs va; memset(&va, 0, sizeof(va));
+    va.theta_pad_n = c->net.theta_pad_n; va.nhid = c->net.nhid;
+    HpvBwdArgs ba; memset(&ba, 0, sizeof(ba)); ba.v = va;
+    int best_threads = 0;
+    const int cand[3] = {128, 256, 64};
+    for (int ci = 0; ci < 3; ++ci) {
+        HpvLaunch l; memset(&l, 0, sizeof(l));
+        long long out = 0;
+        l.kind = HPV_K_MLPBWD; l.op = 2; l.block = cand[ci]; l.bwd = &ba; l.out = &out;
+        HPV_CK(hpv_dispatch(k, l));
+        const size_t sm = (size_t)out;
+        if (sm > 227 * 1024) continue;
+        l.op = 1; l.smem = sm;
+        cudaError_t e = hpv_dispatch(k, l);
+        if (e != cudaSuccess) { cudaGetLastError(); continue; }
+        const int threads = (int)out * cand[ci];
+        if (threads > best_threads) { best_threads = threads; block = cand[ci]; ctas_per_sm = (int)out; smem = sm; }
+    }
+    if (!best_threads) return fail(c, HPV_ERR_LIMIT, "network too deep/wide for the shared-memory plan of the MLP reverse sweep");
+    return HPV_OK;
+}
+
+int ensure_ready(hpv_ctx* c) {
+    if (c->ready) return HPV_OK;
+    if (!c->have_net) return fail(c, HPV_ERR_STATE, "hpv_set_network has not been called");
+    if (!c->have_quad) return fail(c, HPV_ERR_STATE, "hpv_set_quadrature has not been called");
+    if (!c->have_tabs) return fail(c, HPV_ERR_STATE, "hpv_set_test_tables has not been called");
+    if (!c->have_form) return fail(c, HPV_ERR_STATE, "hpv_set_form has not been called");
+    if (!c->have_el) return fail(c, HPV_ERR_STATE, "hpv_set_elements has not been called");
+    const int pdim = (c->problem == HPV_POISSON1D) ? 1 : 2;
+    if (pdim != c->net.dim) return fail(c, HPV_ERR_ARG, "network input dimension does not match the problem");
+    if (c->ntx > c->N || (pdim == 2 && c->nty > c->N)) return fail(c, HPV_ERR_ARG, "more test functions requested than the tables hold");
+    if (c->form.fold_boundary) {
+        if (!c->have_d1b) return fail(c, HPV_ERR_STATE, "Poisson-1D var_form 3 needs d1_bound in hpv_set_test_tables");
+        if (fabs(c->xi[0] + 1.0) > 1e-12 || fabs(c->xi[c->Q - 1] - 1.0) > 1e-12)
+            return fail(c, HPV_ERR_ARG, "Poisson-1D var_form 3 needs Gauss-Lobatto nodes (xi[0] = -1, xi[Q-1] = 1)");
+    }
+    std::vector<float> tabs[HPV_NTAB];
+    hpv_build_tables(c->Q, c->N, c->w.data(), c->T.data(), c->D1.data(), c->D2.data(),
+                     c->have_d1b ? c->d1b.data() : nullptr, c->form.fold_boundary, tabs);
+    for (int t = 0; t < HPV_NTAB; ++t) { int r = upload(c, c->tab[t], tabs[t]); if (r) return r; }
+    std::vector<float> xi1(c->Q);
+    for (int q = 0; q < c->Q; ++q) xi1[q] = (float)(c->xi[q] + 1.0);
+    { int r = upload(c, c->xi1, xi1); if (r) return r; }
+
+    // forward launch plan
+    HpvVarArgs a; fill_var_args(c, a);
+    const HpvFwdSmem fs = hpv_fwd_smem(a);
+    c->fwd_smem = (size_t)fs.total * 4;
+    if (c->fwd_smem > 227 * 1024) return fail(c, HPV_ERR_LIMIT, "forward kernel shared-memory plan exceeds 227 KB (reduce Q)");
+    const HpvKernelKey k = key_of(c, c->form.mx, c->form.my);
+    {
+        HpvLaunch l; memset(&l, 0, sizeof(l));
+        long long out = 0;
+        l.kind = HPV_K_VARFWD; l.op = 1; l.block = HPV_THREADS; l.smem = c->fwd_smem; l.out = &out;
+        HPV_CK(hpv_dispatch(k, l));
+        if (out < 1) return fail(c, HPV_ERR_LIMIT, "forward kernel cannot be resident on an SM");
+        c->fwd_ctas_per_sm = (int)out;
+    }
+    const int rows = (c->net.dim == 2) ? c->Q : 1;
+    hpv_partition(c->part, c->n_el, rows * c->Q, HPV_THREADS, c->n_sm * c->fwd_ctas_per_sm);
+    { int r;
+      if ((r = upload(c, c->cta_tile_begin, c->part.cta_tile_begin))) return r;
+      if ((r = upload(c, c->el_first_cta, c->part.el_first_cta))) return r;
+      if ((r = upload(c, c->el_part_off, c->part.el_part_off))) return r;
+      if ((r = upload(c, c->el_nparts, c->part.el_nparts))) return r; }
+    HPV_CK(c->Upart.alloc((size_t)c->part.total_parts * HPV_NP * HPV_NP));
+    HPV_CK(c->counters.alloc(c->n_el + 1));
+    HPV_CK(cudaMemsetAsync(c->counters.p, 0, (c->n_el + 1) * sizeof(unsigned int), c->stream));
+    HPV_CK(c->Res.alloc((size_t)c->n_el * c->nty * c->ntx));
+    HPV_CK(c->el_loss.alloc(c->n_el));
+    HPV_CK(c->loss.alloc(1));
+
+    // backward launch plan
+    { int r = plan_bwd(c, c->form.mx, c->form.my, c->bwd_block, c->bwd_ctas_per_sm, c->bwd_smem); if (r) return r; }
+    c->bwd_grid = c->n_sm * c->bwd_ctas_per_sm;
+    const long long npts = (long long)c->n_el * rows * c->Q;
+    const long long ntiles = (npts + c->bwd_block - 1) / c->bwd_block;
+    if (c->bwd_grid > ntiles) c->bwd_grid = (int)ntiles;
+    c->grad_stride = hpv_align4(c->net.theta_pad_n + 1);
+    int max_grid = c->bwd_grid;
+    if (max_grid < c->n_sm * 4) max_grid = c->n_sm * 4;          // point-loss launches reuse the buffer
+    HPV_CK(c->grad_part.alloc((size_t)max_grid * c->grad_stride));
+    HPV_CK(c->Gbar.alloc((size_t)c->form.n_terms * npts));
+    c->slabs_per_el = (rows + HPV_ADJ_RS - 1) / HPV_ADJ_RS;
+    c->adj_grid = c->n_el * c->slabs_per_el;
+    c->adj_smem = (size_t)hpv_adj_smem(a).total * 4;
+    if (c->adj_smem > 227 * 1024) return fail(c, HPV_ERR_LIMIT, "adjoint projection shared-memory plan exceeds 227 KB");
+    c->loss_off = hpv_align4(c->net.theta_pad_n + 1);
+    HPV_CK(c->redbuf.alloc(c->loss_off + 8));
+    HPV_CK(cudaMemsetAsync(c->redbuf.p, 0, (c->loss_off + 8) * sizeof(float), c->stream));
+    c->ready = true;
+    return HPV_OK;
+}
+
+int launch_forward(hpv_ctx* c) {
+    HpvVarArgs a; fill_var_args(c, a);
+    HpvLaunch l; memset(&l, 0, sizeof(l));
+    l.kind = HPV_K_VARFWD; l.op = 0; l.grid = c->part.n_ctas; l.block = HPV_THREADS; l.smem = c->fwd_smem;
+    l.stream = c->stream; l.var = &a;
+    HPV_CK(hpv_dispatch(key_of(c, c->form.mx, c->form.my), l));
+    c->launches += 1;
+    return HPV_OK;
+}
+
+int launch_adjproj(hpv_ctx* c) {
+    HpvAdjArgs aa; fill_var_args(c, aa.v);
+    aa.Gbar = c->Gbar.p; aa.slabs_per_el = c->slabs_per_el;
+    HPV_CK(hpv_launch_adjproj(aa, c->adj_grid, c->adj_smem, c->stream));
+    c->launches += 1;
+    return HPV_OK;
+}
+
+int launch_mlpbwd_var(hpv_ctx* c) {
+    HpvBwdArgs ba; fill_var_args(c, ba.v);
+    const int rows = (c->net.dim == 2) ? c->Q : 1;
+    ba.Gbar = c->Gbar.p; ba.n_points = c->n_el * rows * c->Q;
+    ba.n_tiles = (ba.n_points + c->bwd_block - 1) / c->bwd_block; ba.pts = nullptr;
+    HpvLaunch l; memset(&l, 0, sizeof(l));
+    l.kind = HPV_K_MLPBWD; l.op = 0; l.grid = c->bwd_grid; l.block = c->bwd_block; l.smem = c->bwd_smem;
+    l.stream = c->stream; l.bwd = &ba;
+    HPV_CK(hpv_dispatch(key_of(c, c->form.mx, c->form.my), l));
+    c->launches += 1;
+    return HPV_OK;
+}
+
+int launch_gradreduce(hpv_ctx* c, int n_parts, int accumulate) {
+    HpvGradReduceArgs g;
+    g.grad_part = c->grad_part.p; g.n_parts = n_parts; g.stride = c->grad_stride; g.n = c->net.theta_pad_n + 1;
+    g.grad_pad = c->redbuf.p; g.accumulate = accumulate;
+    HPV_CK(hpv_launch_gradreduce(g, c->stream));
+    c->launches += 1;
+    return HPV_OK;
+}
+
+int launch_points(hpv_ctx* c, int mx, int my, int n, const float* pts, float* u, float* d1, float* d2,
+                  PointSet* ps, bool want_adjoint) {
+    HpvPointArgs p; memset(&p, 0, sizeof(p));
+    p.theta_pad = c->theta_pad.p; p.theta_pad_n = c->net.theta_pad_n; p.nhid = c->net.nhid; p.eps = c->eps.p;
+    p.n = n; p.pts = pts; p.out_u = u; p.out_d1 = d1; p.out_d2 = d2;
+    int grid = (n + HPV_THREADS - 1) / HPV_THREADS;
+    if (grid > c->n_sm * 4) grid = c->n_sm * 4;
+    if (grid < 1) grid = 1;
+    float* gbar = nullptr;
+    if (ps) {
+        for (int f = 0; f < HPV_NFIELDS; ++f) { p.a0[f] = ps->a0[f]; p.a1[f] = ps->a1[f]; }
+        p.target = ps->target.p; p.weight = ps->weight; p.resid = ps->resid.p; p.blk_loss = ps->blk_loss.p;
+        ps->n_ctas = grid;
+        if (want_adjoint) gbar = ps->gbar.p;
+    }
+    p.n_ctas = grid;
+    HpvLaunch l; memset(&l, 0, sizeof(l));
+    l.kind = HPV_K_POINTS; l.op = 0; l.grid = grid; l.block = HPV_THREADS;
+    l.smem = (size_t)(hpv_align4(c->net.theta_pad_n) + HPV_THREADS) * 4;
+    l.stream = c->stream; l.pts = &p; l.gbar_out = gbar;
+    HPV_CK(hpv_dispatch(key_of(c, mx, my), l));
+    c->launches += 1;
+    return HPV_OK;
+}
+
+int launch_mlpbwd_points(hpv_ctx* c, PointSet& ps, int& grid_out) {
+    int block = 0, cps = 0; size_t smem = 0;
+    { int r = plan_bwd(c, ps.mx, ps.my, block, cps, smem); if (r) return r; }
+    HpvBwdArgs ba; memset(&ba, 0, sizeof(ba));
+    HpvVarArgs& a = ba.v;
+    a.theta_pad = c->theta_pad.p; a.theta_pad_n = c->net.theta_pad_n; a.nhid = c->net.nhid; a.eps = c->eps.p;
+    a.Q = 1; a.rows = 1; a.n_terms = 1;
+    a.terms[0] = hpv_term_zero();
+    for (int f = 0; f < HPV_NFIELDS; ++f) { a.terms[0].a0[f] = ps.a0[f]; a.terms[0].a1[f] = ps.a1[f]; }
+    a.grad_part = c->grad_part.p; a.grad_stride = c->grad_stride;
+    ba.Gbar = ps.gbar.p; ba.n_points = ps.n; ba.n_tiles = (ps.n + block - 1) / block; ba.pts = ps.pts.p;
+    int grid = c->n_sm * cps;
+    if (grid > ba.n_tiles) grid = ba.n_tiles;
+    if ((size_t)grid * c->grad_stride > c->grad_part.n) grid = (int)(c->grad_part.n / c->grad_stride);
+    HpvLaunch l; memset(&l, 0, sizeof(l));
+    l.kind = HPV_K_MLPBWD; l.op = 0; l.grid = grid; l.block = block; l.smem = smem; l.stream = c->stream; l.bwd = &ba;
+    HPV_CK(hpv_dispatch(key_of(c, ps.mx, ps.my), l));
+    c->launches += 1;
+    grid_out = grid;
+    return HPV_OK;
+}
+
+struct LossArgs {
+    const double* lossv; float wv; int use_v;
+    const float* blk[HPV_MAX_POINT_SETS]; int nblk[HPV_MAX_POINT_SETS];
+    float* out;     // [8]: total, lossv, point losses
+};
+
+__global__ void hpv_losses_kernel(const LossArgs a) {
+    const int lane = threadIdx.x;
+    float total = 0.0f;
+    float lv = a.use_v ? (float)a.lossv[0] : 0.0f;
+    total = a.wv * lv;
+    float pl[HPV_MAX_POINT_SETS];
+    for (int s = 0; s < HPV_MAX_POINT_SETS; ++s) {
+        float acc = 0.0f;
+        if (a.blk[s]) for (int i = lane; i < a.nblk[s]; i += 32) acc += a.blk[s][i];
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        pl[s] = acc;
+        total += acc;
+    }
+    if (lane == 0) {
+        a.out[0] = total; a.out[1] = lv;
+        for (int s = 0; s < HPV_MAX_POINT_SETS; ++s) a.out[2 + s] = pl[s];
+    }
+}
+
+int need_net(hpv_ctx* c) {
+    if (!c) return HPV_ERR_ARG;
+    if (!c->have_net) return fail(c, HPV_ERR_STATE, "hpv_set_network has not been called");
+    return HPV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hpv_abi_version(void) { return 1; }
+
+int hpv_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int hpv_create(hpv_ctx** out, int device) {
+    hpv_ctx* c = nullptr;
+    if (!out) return fail(c, HPV_ERR_ARG, "ctx output pointer is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(c, HPV_ERR_CUDA, "no CUDA device: libhpv has no CPU path");
+    }
+    if (device < 0 || device >= n) return fail(c, HPV_ERR_ARG, "device index out of range");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(c, HPV_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(c, HPV_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+    if (prop.major != 10) return fail(c, HPV_ERR_CUDA, "libhpv is built for sm_100a (B200) only");
+    hpv_ctx* ctx = new hpv_ctx();
+    ctx->device = device; ctx->n_sm = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ctx; return fail(c, HPV_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return HPV_OK;
+}
+
+void hpv_destroy(hpv_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->theta_pad.release(); c->eps.release(); c->master.release(); c->adam_m.release(); c->adam_v.release();
+    c->grad_out.release(); c->pad_index.release(); c->step.release(); c->xi1.release();
+    for (int t = 0; t < HPV_NTAB; ++t) c->tab[t].release();
+    c->geom.release(); c->F.release(); c->Res.release(); c->el_loss.release(); c->Upart.release(); c->Gbar.release();
+    c->ntest.release(); c->cta_tile_begin.release(); c->el_first_cta.release(); c->el_part_off.release();
+    c->el_nparts.release(); c->counters.release(); c->loss.release(); c->grad_part.release(); c->redbuf.release();
+    for (int s = 0; s < HPV_MAX_POINT_SETS; ++s) {
+        c->ps[s].pts.release(); c->ps[s].target.release(); c->ps[s].resid.release(); c->ps[s].gbar.release();
+        c->ps[s].blk_loss.release();
+    }
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char* hpv_last_error(hpv_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int hpv_set_stream(hpv_ctx* c, void* s) {
+    if (!c) return HPV_ERR_ARG;
+    HPV_CK(cudaSetDevice(c->device));
+    HPV_CK(cudaStreamSynchronize(c->stream));
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return HPV_OK;
+}
+
+int hpv_sync(hpv_ctx* c) {
+    if (!c) return HPV_ERR_ARG;
+    HPV_CK(cudaSetDevice(c->device));
+    HPV_CK(cudaStreamSynchronize(c->stream));
+    return HPV_OK;
+}
+
+int hpv_set_network(hpv_ctx* c, int dim, const int* layers, int n_layers, int act) {
+    if (!c || !layers) return fail(c, HPV_ERR_ARG, "NULL argument");
+    HPV_CK(cudaSetDevice(c->device));
+    std::string err;
+    HpvNet net;
+    if (!hpv_net_setup(net, dim, layers, n_layers, act, err)) return fail(c, HPV_ERR_ARG, err);
+    c->net = net; c->have_net = true; c->ready = false;
+    const int P = net.n_theta;
+    HPV_CK(c->theta_pad.alloc(net.theta_pad_n));
+    HPV_CK(cudaMemsetAsync(c->theta_pad.p, 0, net.theta_pad_n * sizeof(float), c->stream));
+    HPV_CK(c->eps.alloc(1));
+    HPV_CK(cudaMemsetAsync(c->eps.p, 0, sizeof(float), c->stream));
+    HPV_CK(c->master.alloc(P + 1)); HPV_CK(c->adam_m.alloc(P + 1)); HPV_CK(c->adam_v.alloc(P + 1));
+    HPV_CK(c->grad_out.alloc(P + 1));
+    HPV_CK(cudaMemsetAsync(c->master.p, 0, (P + 1) * sizeof(double), c->stream));
+    HPV_CK(c->step.alloc(1));
+    { int r = upload(c, c->pad_index, net.pad_index); if (r) return r; }
+    for (int s = 0; s < HPV_MAX_POINT_SETS; ++s) c->ps[s].active = false;
+    return hpv_reset_optimizer(c);
+}
+
+int hpv_num_params(hpv_ctx* c) {
+    if (!c || !c->have_net) return HPV_ERR_STATE;
+    return c->net.n_theta;
+}
+
+int hpv_set_params(hpv_ctx* c, const double* theta, int n, double eps) {
+    { int r = need_net(c); if (r) return r; }
+    if (!theta || n != c->net.n_theta) return fail(c, HPV_ERR_ARG, "theta must hold hpv_num_params() values");
+    HPV_CK(cudaSetDevice(c->device));
+    std::vector<float>& pad = c->host_f32;
+    hpv_pad_theta(c->net, theta, pad);
+    pad.push_back((float)eps);
+    std::vector<double>& m = c->host_f64;
+    m.assign(theta, theta + n); m.push_back(eps);
+    HPV_CK(cudaMemcpyAsync(c->theta_pad.p, pad.data(), c->net.theta_pad_n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    HPV_CK(cudaMemcpyAsync(c->eps.p, pad.data() + c->net.theta_pad_n, sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    HPV_CK(cudaMemcpyAsync(c->master.p, m.data(), (n + 1) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    HPV_CK(cudaStreamSynchronize(c->stream));
+    return HPV_OK;
+}
+
+int hpv_get_params(hpv_ctx* c, double* theta, int n, double* eps) {
+    { int r = need_net(c); if (r) return r; }
+    if (!theta || n != c->net.n_theta) return fail(c, HPV_ERR_ARG, "theta must hold hpv_num_params() values");
+    HPV_CK(cudaSetDevice(c->device));
+    std::vector<double>& m = c->host_f64;
+    m.resize(n + 1);
+    HPV_CK(cudaMemcpyAsync(m.data(), c->master.p, (n + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    HPV_CK(cudaStreamSynchronize(c->stream));
+    memcpy(theta, m.data(), n * sizeof(double));
+    if (eps) *eps = m[n];
+    return HPV_OK;
+}
+
+int hpv_set_quadrature(hpv_ctx* c, int Q, const double* xi, const double* w) {
+    if (!c || !xi || !w) return fail(c, HPV_ERR_ARG, "NULL argument");
+    if (Q < 2 || Q > HPV_QMAX) return fail(c, HPV_ERR_LIMIT, "Q must be in [2, 128]");
+    c->Q = Q; c->xi.assign(xi, xi + Q); c->w.assign(w, w + Q);
+    c->have_quad = true; c->have_tabs = false; c->ready = false;
+    return HPV_OK;
+}
+
+int hpv_set_test_tables(hpv_ctx* c, int N, const double* T, const double* D1, const double* D2, const double* d1b) {
+    if (!c || !T) return fail(c, HPV_ERR_ARG, "NULL argument");
+    if (!c->have_quad) return fail(c, HPV_ERR_STATE, "hpv_set_quadrature must come first");
+    if (N < 1 || N > HPV_NP) return fail(c, HPV_ERR_LIMIT, "N must be in [1, 64]");
+    const size_t n = (size_t)N * c->Q;
+    c->N = N; c->T.assign(T, T + n);
+    if (D1) c->D1.assign(D1, D1 + n); else c->D1.assign(n, 0.0);
+    if (D2) c->D2.assign(D2, D2 + n); else c->D2.assign(n, 0.0);
+    c->have_d1b = d1b != nullptr;
+    if (d1b) c->d1b.assign(d1b, d1b + 2 * (size_t)N);
+    c->have_tabs = true; c->ready = false;
+    return HPV_OK;
+}
+
+int hpv_set_form(hpv_ctx* c, int problem, int var_form, double V) {
+    if (!c) return HPV_ERR_ARG;
+    std::string err;
+    HpvForm fm;
+    if (!hpv_form_setup(fm, problem, var_form, V, err)) return fail(c, HPV_ERR_ARG, err);
+    c->form = fm; c->problem = problem; c->var_form = var_form; c->V = V;
+    c->have_form = true; c->ready = false;
+    return HPV_OK;
+}
+
+int hpv_set_elements(hpv_ctx* c, int n_el, const double* lo, const double* hi, const int* ntest, int ntx, int nty,
+                     const double* F_ext) {
+    { int r = need_net(c); if (r) return r; }
+    if (!lo || !hi) return fail(c, HPV_ERR_ARG, "NULL element corners");
+    if (n_el < 1) return fail(c, HPV_ERR_ARG, "n_el must be >= 1 (an empty element batch has no loss)");
+    const int dim = c->net.dim;
+    if (dim == 1) nty = 1;
+    if (ntx < 1 || ntx > HPV_NP || nty < 1 || nty > HPV_NP) return fail(c, HPV_ERR_LIMIT, "ntx, nty must be in [1, 64]");
+    HPV_CK(cudaSetDevice(c->device));
+    std::vector<float> geom((size_t)n_el * 4);
+    std::vector<int> nt((size_t)n_el * 2);
+    for (int e = 0; e < n_el; ++e) {
+        const double lx = lo[(size_t)e * dim], hx = hi[(size_t)e * dim];
+        if (!(hx > lx)) return fail(c, HPV_ERR_ARG, "element with non-positive width");
+        geom[4 * e + 0] = (float)lx; geom[4 * e + 1] = (float)((hx - lx) / 2);
+        geom[4 * e + 2] = 0.0f; geom[4 * e + 3] = 1.0f;
+        if (dim == 2) {
+            const double ly = lo[(size_t)e * dim + 1], hy = hi[(size_t)e * dim + 1];
+            if (!(hy > ly)) return fail(c, HPV_ERR_ARG, "element with non-positive height");
+            geom[4 * e + 2] = (float)ly; geom[4 * e + 3] = (float)((hy - ly) / 2);
+        }
+        int ex = ntx, ey = nty;
+        if (ntest) { ex = ntest[(size_t)e * dim]; ey = (dim == 2) ? ntest[(size_t)e * dim + 1] : 1; }
+        if (ex < 1 || ex > ntx || ey < 1 || ey > nty) return fail(c, HPV_ERR_ARG, "per-element ntest out of [1, ntx] x [1, nty]");
+        nt[2 * e + 0] = ex; nt[2 * e + 1] = ey;
+    }
+    c->n_el = n_el; c->ntx = ntx; c->nty = nty; c->has_F = F_ext != nullptr;
+    { int r;
+      if ((r = upload(c, c->geom, geom))) return r;
+      if ((r = upload(c, c->ntest, nt))) return r; }
+    const size_t nf = (size_t)n_el * nty * ntx;
+    HPV_CK(c->F.alloc(nf));
+    if (F_ext) {
+        std::vector<float> f(nf);
+        for (size_t i = 0; i < nf; ++i) f[i] = (float)F_ext[i];
+        int r = upload(c, c->F, f); if (r) return r;
+    }
+    c->have_el = true; c->ready = false;
+    return HPV_OK;
+}
+
+int hpv_update_rhs_f32(hpv_ctx* c, const float* F) {
+    if (!c || !F) return fail(c, HPV_ERR_ARG, "NULL argument");
+    if (!c->have_el || !c->has_F) return fail(c, HPV_ERR_STATE, "no element batch with a right-hand side is set");
+    HPV_CK(cudaSetDevice(c->device));
+    HPV_CK(cudaMemcpyAsync(c->F.p, F, (size_t)c->n_el * c->nty * c->ntx * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    return HPV_OK;
+}
+
+int hpv_varloss_forward(hpv_ctx* c, double* lossv, float* residual, double* el_loss) {
+    if (!c) return HPV_ERR_ARG;
+    HPV_CK(cudaSetDevice(c->device));
+    { int r = ensure_ready(c); if (r) return r; }
+    { int r = launch_forward(c); if (r) return r; }
+    double lv = 0.0;
+    HPV_CK(cudaMemcpyAsync(&lv, c->loss.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (residual)
+        HPV_CK(cudaMemcpyAsync(residual, c->Res.p, (size_t)c->n_el * c->nty * c->ntx * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (el_loss) {
+        c->host_f32.resize(c->n_el);
+        HPV_CK(cudaMemcpyAsync(c->host_f32.data(), c->el_loss.p, c->n_el * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    HPV_CK(cudaStreamSynchronize(c->stream));
+    if (lossv) *lossv = lv;
+    if (el_loss) for (int e = 0; e < c->n_el; ++e) el_loss[e] = c->host_f32[e];
+    return HPV_OK;
+}
+
+static int unpad_grad(hpv_ctx* c, int update) {
+    HpvAdamArgs a; memset(&a, 0, sizeof(a));
+    a.grad_pad = c->redbuf.p; a.pad_index = c->pad_index.p; a.n_theta = c->net.n_theta; a.theta_pad_n = c->net.theta_pad_n;
+    a.theta = c->master.p; a.m = c->adam_m.p; a.v = c->adam_v.p; a.theta_pad = c->theta_pad.p; a.eps = c->eps.p;
+    a.grad_out = c->grad_out.p; a.train_eps = c->train_eps;
+    a.lr = (float)c->lr; a.b1 = (float)c->b1; a.b2 = (float)c->b2; a.eps_hat = (float)c->eps_hat;
+    a.step = c->step.p; a.step_rw = c->step.p; a.update = update;
+    HPV_CK(hpv_launch_adam(a, c->stream));
+    c->launches += update ? 2 : 1;
+    return HPV_OK;
+}
+
+static int read_grad(hpv_ctx* c, double* grad_theta, int n, double* grad_eps) {
+    if (!grad_theta || n != c->net.n_theta) return fail(c, HPV_ERR_ARG, "grad_theta must hold hpv_num_params() values");
+    { int r = unpad_grad(c, 0); if (r) return r; }
+    std::vector<double>& g = c->host_f64;
+    g.resize(n + 1);
+    HPV_CK(cudaMemcpyAsync(g.data(), c->grad_out.p, (n + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    HPV_CK(cudaStreamSynchronize(c->stream));
+    memcpy(grad_theta, g.data(), n * sizeof(double));
+    if (grad_eps) *grad_eps = g[n];
+    return HPV_OK;
+}
+
+int hpv_varloss_backward(hpv_ctx* c, double* grad_theta, int n, double* grad_eps) {
+    if (!c) return HPV_ERR_ARG;
+    HPV_CK(cudaSetDevice(c->device));
+    { int r = ensure_ready(c); if (r) return r; }
+    const double wv_saved = c->wv;
+    c->wv = 1.0;
+    int r = launch_adjproj(c);
+    if (!r) r = launch_mlpbwd_var(c);
+    if (!r) r = launch_gradreduce(c, c->bwd_grid, 0);
+    c->wv = wv_saved;
+    if (r) return r;
+    return read_grad(c, grad_theta, n, grad_eps);
+}
+
+int hpv_net_u(hpv_ctx* c, int n, const double* pts, double* u, double* d1, double* d2) {
+    { int r = need_net(c); if (r) return r; }
+    if (n < 0 || (n > 0 && !pts)) return fail(c, HPV_ERR_ARG, "bad point array");
+    if (n == 0) return HPV_OK;
+    HPV_CK(cudaSetDevice(c->device));
+    const int dim = c->net.dim;
+    std::vector<float> hp((size_t)n * dim);
+    for (size_t i = 0; i < hp.size(); ++i) hp[i] = (float)pts[i];
+    DevBuf<float> dp, du, dd1, dd2;
+    HPV_CK(dp.alloc(hp.size()));
+    HPV_CK(cudaMemcpyAsync(dp.p, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (u) HPV_CK(du.alloc(n));
+    if (d1) HPV_CK(dd1.alloc((size_t)n * dim));
+    if (d2) HPV_CK(dd2.alloc((size_t)n * dim));
+    const int m = d2 ? 2 : (d1 ? 1 : 0);
+    int r = launch_points(c, m, m, n, dp.p, du.p, dd1.p, dd2.p, nullptr, false);
+    std::vector<float> out;
+    auto fetch = [&](DevBuf<float>& b, double* dst, size_t cnt) -> cudaError_t {
+        out.resize(cnt);
+        cudaError_t e = cudaMemcpyAsync(out.data(), b.p, cnt * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e == cudaSuccess) for (size_t i = 0; i < cnt; ++i) dst[i] = out[i];
+        return e;
+    };
+    cudaError_t e = cudaSuccess;
+    if (!r && u) e = fetch(du, u, n);
+    if (!r && e == cudaSuccess && d1) e = fetch(dd1, d1, (size_t)n * dim);
+    if (!r && e == cudaSuccess && d2) e = fetch(dd2, d2, (size_t)n * dim);
+    cudaStreamSynchronize(c->stream);
+    dp.release(); du.release(); dd1.release(); dd2.release();
+    if (r) return r;
+    if (e != cudaSuccess) return fail(c, HPV_ERR_CUDA, std::string("hpv_net_u: ") + cudaGetErrorString(e));
+    return HPV_OK;
+}
+
+int hpv_set_point_loss(hpv_ctx* c, int slot, int n, const double* pts, const double* target, const double* a0,
+                       const double* a1, double weight) {
+    { int r = need_net(c); if (r) return r; }
+    if (slot < 0 || slot >= HPV_MAX_POINT_SETS) return fail(c, HPV_ERR_ARG, "slot out of range");
+    PointSet& ps = c->ps[slot];
+    if (n == 0) { ps.active = false; ps.n = 0; return HPV_OK; }
+    if (n < 0 || !pts || !target || !a0) return fail(c, HPV_ERR_ARG, "bad point-loss arguments");
+    HPV_CK(cudaSetDevice(c->device));
+    const int dim = c->net.dim;
+    std::vector<float> hp((size_t)n * dim), ht(n);
+    for (size_t i = 0; i < hp.size(); ++i) hp[i] = (float)pts[i];
+    for (int i = 0; i < n; ++i) ht[i] = (float)target[i];
+    { int r;
+      if ((r = upload(c, ps.pts, hp))) return r;
+      if ((r = upload(c, ps.target, ht))) return r; }
+    HPV_CK(ps.resid.alloc(n)); HPV_CK(ps.gbar.alloc(n)); HPV_CK(ps.blk_loss.alloc((size_t)c->n_sm * 4));
+    for (int f = 0; f < HPV_NFIELDS; ++f) { ps.a0[f] = (float)a0[f]; ps.a1[f] = a1 ? (float)a1[f] : 0.0f; }
+    if (dim == 1 && (ps.a0[2] != 0 || ps.a0[4] != 0 || ps.a1[2] != 0 || ps.a1[4] != 0))
+        return fail(c, HPV_ERR_ARG, "y-derivative fields requested for a 1-D network");
+    ps.weight = (float)weight; ps.n = n; ps.mx = 0; ps.my = 0;
+    hpv_mode_of_coef(dim, ps.a0, ps.a1, ps.mx, ps.my);
+    hpv_canon_mode(dim, ps.mx, ps.my);
+    ps.active = true;
+    return HPV_OK;
+}
+
+int hpv_point_loss_forward(hpv_ctx* c, int slot, double* loss, double* resid) {
+    { int r = need_net(c); if (r) return r; }
+    if (slot < 0 || slot >= HPV_MAX_POINT_SETS || !c->ps[slot].active) return fail(c, HPV_ERR_ARG, "point-loss slot is not set");
+    HPV_CK(cudaSetDevice(c->device));
+    PointSet& ps = c->ps[slot];
+    { int r = launch_points(c, ps.mx, ps.my, ps.n, ps.pts.p, nullptr, nullptr, nullptr, &ps, false); if (r) return r; }
+    std::vector<float>& h = c->host_f32;
+    h.resize(ps.n_ctas + ps.n);
+    HPV_CK(cudaMemcpyAsync(h.data(), ps.blk_loss.p, ps.n_ctas * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    HPV_CK(cudaMemcpyAsync(h.data() + ps.n_ctas, ps.resid.p, ps.n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    HPV_CK(cudaStreamSynchronize(c->stream));
+    double acc = 0.0;
+    for (int i = 0; i < ps.n_ctas; ++i) acc += h[i];
+    if (loss) *loss = acc;
+    if (resid) for (int i = 0; i < ps.n; ++i) resid[i] = h[ps.n_ctas + i];
+    return HPV_OK;
+}
+
+int hpv_configure_training(hpv_ctx* c, double wv, unsigned mask, int train_eps, double lr, double b1, double b2,
+                           double eps_hat) {
+    if (!c) return HPV_ERR_ARG;
+    c->wv = wv; c->mask = mask; c->train_eps = train_eps; c->lr = lr; c->b1 = b1; c->b2 = b2; c->eps_hat = eps_hat;
+    return HPV_OK;
+}
+
+int hpv_loss_and_grad(hpv_ctx* c) {
+    { int r = need_net(c); if (r) return r; }
+    HPV_CK(cudaSetDevice(c->device));
+    const bool use_v = c->wv != 0.0;
+    if (use_v || !c->redbuf.p) { int r = ensure_ready(c); if (r) return r; }
+    int acc = 0;
+    if (use_v) {
+        int r = launch_forward(c);
+        if (!r) r = launch_adjproj(c);
+        if (!r) r = launch_mlpbwd_var(c);
+        if (!r) r = launch_gradreduce(c, c->bwd_grid, 0);
+        if (r) return r;
+        acc = 1;
+    }
+    LossArgs la; memset(&la, 0, sizeof(la));
+    la.lossv = c->loss.p; la.wv = (float)c->wv; la.use_v = use_v ? 1 : 0; la.out = c->redbuf.p + c->loss_off;
+    for (int s = 0; s < HPV_MAX_POINT_SETS; ++s) {
+        if (!(c->mask & (1u << s)) || !c->ps[s].active) continue;
+        PointSet& ps = c->ps[s];
+        int grid = 0;
+        int r = launch_points(c, ps.mx, ps.my, ps.n, ps.pts.p, nullptr, nullptr, nullptr, &ps, true);
+        if (!r) r = launch_mlpbwd_points(c, ps, grid);
+        if (!r) r = launch_gradreduce(c, grid, acc);
+        if (r) return r;
+        acc = 1;
+        la.blk[s] = ps.blk_loss.p; la.nblk[s] = ps.n_ctas;
+    }
+    if (!acc) HPV_CK(cudaMemsetAsync(c->redbuf.p, 0, c->loss_off * sizeof(float), c->stream));
+    hpv_losses_kernel<<<1, 32, 0, c->stream>>>(la);
+    HPV_CK(cudaGetLastError());
+    c->launches += 1;
+    return HPV_OK;
+}
+
+int hpv_reduce_buffer(hpv_ctx* c, void** p, int* n) {
+    if (!c || !p || !n) return HPV_ERR_ARG;
+    HPV_CK(cudaSetDevice(c->device));
+    { int r = ensure_ready(c); if (r) return r; }
+    *p = c->redbuf.p; *n = c->loss_off + 8;
+    return HPV_OK;
+}
+
+int hpv_adam_step(hpv_ctx* c) {
+    { int r = need_net(c); if (r) return r; }
+    if (!c->redbuf.p) return fail(c, HPV_ERR_STATE, "hpv_loss_and_grad has not been called");
+    HPV_CK(cudaSetDevice(c->device));
+    return unpad_grad(c, 1);
+}
+
+int hpv_read_losses(hpv_ctx* c, double* out, int n) {
+    if (!c || !out || n < 1) return HPV_ERR_ARG;
+    if (!c->redbuf.p) return fail(c, HPV_ERR_STATE, "hpv_loss_and_grad has not been called");
+    HPV_CK(cudaSetDevice(c->device));
+    float h[8];
+    HPV_CK(cudaMemcpyAsync(h, c->redbuf.p + c->loss_off, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    HPV_CK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n && i < 8; ++i) out[i] = h[i];
+    return HPV_OK;
+}
+
+int hpv_read_grad(hpv_ctx* c, double* g, int n, double* ge) {
+    { int r = need_net(c); if (r) return r; }
+    if (!c->redbuf.p) return fail(c, HPV_ERR_STATE, "hpv_loss_and_grad has not been called");
+    HPV_CK(cudaSetDevice(c->device));
+    return read_grad(c, g, n, ge);
+}
+
+int hpv_reset_optimizer(hpv_ctx* c) {
+    { int r = need_net(c); if (r) return r; }
+    HPV_CK(cudaSetDevice(c->device));
+    const int P = c->net.n_theta;
+    HPV_CK(cudaMemsetAsync(c->adam_m.p, 0, (P + 1) * sizeof(double), c->stream));
+    HPV_CK(cudaMemsetAsync(c->adam_v.p, 0, (P + 1) * sizeof(double), c->stream));
+    HPV_CK(cudaMemsetAsync(c->step.p, 0, sizeof(int), c->stream));
+    return HPV_OK;
+}
+
+int hpv_train_steps(hpv_ctx* c, int nsteps, double* hist) {
+    { int r = need_net(c); if (r) return r; }
+    if (nsteps < 0) return fail(c, HPV_ERR_ARG, "nsteps < 0");
+    DevBuf<float> dh;
+    if (hist && nsteps) HPV_CK(dh.alloc(nsteps));
+    for (int it = 0; it < nsteps; ++it) {
+        int r = hpv_loss_and_grad(c);
+        if (!r && hist)
+            HPV_CK(cudaMemcpyAsync(dh.p + it, c->redbuf.p + c->loss_off, sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        if (!r) r = hpv_adam_step(c);
+        if (r) { dh.release(); return r; }
+    }
+    if (hist && nsteps) {
+        std::vector<float> h(nsteps);
+        HPV_CK(cudaMemcpyAsync(h.data(), dh.p, nsteps * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        HPV_CK(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < nsteps; ++i) hist[i] = h[i];
+    }
+    dh.release();
+    return HPV_OK;
+}
+
+long long hpv_launch_count(hpv_ctx* c) { return c ? c->launches : 0; }
+
+int hpv_kernel_info(hpv_ctx* c, int* info, int n) {
+    if (!c || !info) return HPV_ERR_ARG;
+    HPV_CK(cudaSetDevice(c->device));
+    { int r = ensure_ready(c); if (r) return r; }
+    const int v[12] = {c->n_sm, c->part.n_ctas, HPV_THREADS, (int)c->fwd_smem, c->fwd_ctas_per_sm,
+                       c->bwd_grid, c->bwd_block, (int)c->bwd_smem, c->bwd_ctas_per_sm,
+                       c->adj_grid, (int)c->adj_smem, c->net.hp};
+    for (int i = 0; i < n && i < 12; ++i) info[i] = v[i];
+    return HPV_OK;
+}
+
+int hpv_probe_fp32_peak(hpv_ctx* c, int variant, double* tflops) {
+    if (!c || !tflops) return HPV_ERR_ARG;
+    HPV_CK(cudaSetDevice(c->device));
+    const int grid = c->n_sm * 8, block = 256, iters = 4096;
+    DevBuf<float> out;
+    HPV_CK(out.alloc((size_t)grid * block));
+    cudaEvent_t e0, e1;
+    HPV_CK(cudaEventCreate(&e0)); HPV_CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) HPV_CK(hpv_launch_ffma_peak(out.p, grid, block, iters, variant, c->stream));
+    const int reps = 10;
+    HPV_CK(cudaEventRecord(e0, c->stream));
+    for (int i = 0; i < reps; ++i) HPV_CK(hpv_launch_ffma_peak(out.p, grid, block, iters, variant, c->stream));
+    HPV_CK(cudaEventRecord(e1, c->stream));
+    HPV_CK(cudaEventSynchronize(e1));
+    float ms = 0.0f;
+    HPV_CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    out.release();
+    const double flops = (double)grid * block * iters * 64.0 * 2.0 * reps;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    return HPV_OK;
+}
+
+int hpv_time_kernel(hpv_ctx* c, int what, int reps, double* usec) {
+    if (!c || !usec || reps < 1) return HPV_ERR_ARG;
+    HPV_CK(cudaSetDevice(c->device));
+    { int r = ensure_ready(c); if (r) return r; }
+    auto run = [&]() -> int {
+        if (what == 0) return launch_forward(c);
+        if (what == 1) return launch_adjproj(c);
+        if (what == 2) return launch_mlpbwd_var(c);
+        int r = launch_gradreduce(c, c->bwd_grid, 0);
+        if (!r) r = unpad_grad(c, 0);
+        return r;
+    };
+    if (what >= 1) { int r = launch_forward(c); if (r) return r; }
+    if (what >= 2) { int r = launch_adjproj(c); if (r) return r; }
+    if (what >= 3) { int r = launch_mlpbwd_var(c); if (r) return r; }
+    for (int i = 0; i < 3; ++i) { int r = run(); if (r) return r; }
+    cudaEvent_t e0, e1;
+    HPV_CK(cudaEventCreate(&e0)); HPV_CK(cudaEventCreate(&e1));
+    HPV_CK(cudaEventRecord(e0, c->stream));
+    for (int i = 0; i < reps; ++i) { int r = run(); if (r) return r; }
+    HPV_CK(cudaEventRecord(e1, c->stream));
+    HPV_CK(cudaEventSynchronize(e1));
+    float ms = 0.0f;
+    HPV_CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *usec = (double)ms * 1e3 / reps;
+    return HPV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,3 @@
+// Kernel instantiations: padded hidden width 20, kind bwd (see hpv_kernels.cuh).
+#include "hpv_kernels.cuh"
+cudaError_t hpv_dispatch_h20_bwd(const HpvKernelKey& k, const HpvLaunch& l) { return hpv_dispatch_hp<20, HPV_K_MLPBWD>(k, l); }

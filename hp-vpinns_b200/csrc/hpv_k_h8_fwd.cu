@@ -1,0 +1,3 @@
+// Kernel instantiations: padded hidden width 8, kind fwd (see hpv_kernels.cuh).
+#include "hpv_kernels.cuh"
+cudaError_t hpv_dispatch_h8_fwd(const HpvKernelKey& k, const HpvLaunch& l) { return hpv_dispatch_hp<8, HPV_K_VARFWD>(k, l); }

@@ -1,0 +1,98 @@
+// __global__ wrappers around the kernel bodies and the per-width dispatch function.  Included by
+// hpv_k_h{8,20,32}_{fwd,bwd,pts}.cu: one translation unit per padded hidden width and kernel kind, so
+// that the build parallelises (each unit instantiates 7 derivative modes x 2 activations).
+#pragma once
+#include "hpv_launch.h"
+
+template <int DIM, int MX, int MY, int HP, int ACT>
+__global__ void __launch_bounds__(HPV_THREADS, 1) hpv_varfwd_kernel(const __grid_constant__ HpvVarArgs a) {
+    extern __shared__ __align__(16) unsigned char hpv_smem[];
+    HpvCta c;
+    c.tid = threadIdx.x; c.nthreads = blockDim.x; c.bid = blockIdx.x; c.nblocks = gridDim.x;
+    c.smem = hpv_smem; c.emu = nullptr;
+    hpv_varfwd_body<DIM, MX, MY, HP, ACT>(c, a);
+}
+
+template <int DIM, int MX, int MY, int HP, int ACT>
+__global__ void __launch_bounds__(HPV_THREADS, 1) hpv_mlpbwd_kernel(const __grid_constant__ HpvBwdArgs a) {
+    extern __shared__ __align__(16) unsigned char hpv_smem[];
+    HpvCta c;
+    c.tid = threadIdx.x; c.nthreads = blockDim.x; c.bid = blockIdx.x; c.nblocks = gridDim.x;
+    c.smem = hpv_smem; c.emu = nullptr;
+    hpv_mlpbwd_body<DIM, MX, MY, HP, ACT>(c, a);
+}
+
+template <int DIM, int MX, int MY, int HP, int ACT>
+__global__ void __launch_bounds__(HPV_THREADS, 1) hpv_points_kernel(const __grid_constant__ HpvPointArgs a, float* gbar_out) {
+    extern __shared__ __align__(16) unsigned char hpv_smem[];
+    HpvCta c;
+    c.tid = threadIdx.x; c.nthreads = blockDim.x; c.bid = blockIdx.x; c.nblocks = gridDim.x;
+    c.smem = hpv_smem; c.emu = nullptr;
+    hpv_points_body<DIM, MX, MY, HP, ACT>(c, a, gbar_out);
+}
+
+template <typename K>
+static cudaError_t hpv_prepare(K kernel, size_t smem) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+template <int DIM, int MX, int MY, int HP, int ACT, int KIND>
+static cudaError_t hpv_do(const HpvLaunch& l) {
+    cudaError_t err = cudaSuccess;
+    if constexpr (KIND == HPV_K_VARFWD) {
+        auto k = hpv_varfwd_kernel<DIM, MX, MY, HP, ACT>;
+        if ((err = hpv_prepare(k, l.smem)) != cudaSuccess) return err;
+        if (l.op == 1) {
+            int n = 0;
+            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, l.block, l.smem);
+            *l.out = n;
+            return err;
+        }
+        k<<<l.grid, l.block, l.smem, l.stream>>>(*l.var);
+    } else if constexpr (KIND == HPV_K_MLPBWD) {
+        auto k = hpv_mlpbwd_kernel<DIM, MX, MY, HP, ACT>;
+        if (l.op == 2) {
+            HpvBwdSmem<DIM, MX, MY, HP> L(l.bwd->v.theta_pad_n, l.bwd->v.nhid, l.block);
+            *l.out = (long long)L.total * 4;
+            return cudaSuccess;
+        }
+        if ((err = hpv_prepare(k, l.smem)) != cudaSuccess) return err;
+        if (l.op == 1) {
+            int n = 0;
+            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, l.block, l.smem);
+            *l.out = n;
+            return err;
+        }
+        k<<<l.grid, l.block, l.smem, l.stream>>>(*l.bwd);
+    } else {
+        auto k = hpv_points_kernel<DIM, MX, MY, HP, ACT>;
+        if ((err = hpv_prepare(k, l.smem)) != cudaSuccess) return err;
+        if (l.op == 1) {
+            int n = 0;
+            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, l.block, l.smem);
+            *l.out = n;
+            return err;
+        }
+        k<<<l.grid, l.block, l.smem, l.stream>>>(*l.pts, l.gbar_out);
+    }
+    return cudaGetLastError();
+}
+
+template <int DIM, int MX, int MY, int HP, int KIND>
+static cudaError_t hpv_do_act(const HpvKernelKey& k, const HpvLaunch& l) {
+    if (k.act == HPV_ACT_TANH) return hpv_do<DIM, MX, MY, HP, HPV_ACT_TANH, KIND>(l);
+    return hpv_do<DIM, MX, MY, HP, HPV_ACT_SIN, KIND>(l);
+}
+
+template <int HP, int KIND>
+static cudaError_t hpv_dispatch_hp(const HpvKernelKey& k, const HpvLaunch& l) {
+    if (k.dim == 1) {
+        if (k.mx == 0) return hpv_do_act<1, 0, 0, HP, KIND>(k, l);
+        if (k.mx == 1) return hpv_do_act<1, 1, 0, HP, KIND>(k, l);
+        return hpv_do_act<1, 2, 0, HP, KIND>(k, l);
+    }
+    if (k.mx == 0 && k.my == 0) return hpv_do_act<2, 0, 0, HP, KIND>(k, l);
+    if (k.mx <= 1 && k.my <= 1) return hpv_do_act<2, 1, 1, HP, KIND>(k, l);
+    if (k.mx == 2 && k.my <= 1) return hpv_do_act<2, 2, 1, HP, KIND>(k, l);
+    return hpv_do_act<2, 2, 2, HP, KIND>(k, l);
+}

@@ -1,0 +1,67 @@
+// Host-side launch interface of the kernels (implemented once per padded hidden width in hpv_kernels_h*.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "hpv_varbwd.cuh"
+#include "hpv_points.cuh"
+
+struct HpvKernelKey { int dim, mx, my, hp, act; };
+
+enum { HPV_K_VARFWD = 0, HPV_K_MLPBWD = 1, HPV_K_POINTS = 2 };
+
+// op: 0 = launch, 1 = query resident CTAs per SM for (block, smem) into *out, 2 = shared memory bytes of the
+// MLP reverse sweep for block size `block` into *out.
+struct HpvLaunch {
+    int kind, op;
+    int grid, block;
+    size_t smem;
+    cudaStream_t stream;
+    const HpvVarArgs* var;
+    const HpvBwdArgs* bwd;
+    const HpvPointArgs* pts;
+    float* gbar_out;
+    long long* out;
+};
+
+#define HPV_DECL(hp) \
+    cudaError_t hpv_dispatch_h##hp##_fwd(const HpvKernelKey& k, const HpvLaunch& l); \
+    cudaError_t hpv_dispatch_h##hp##_bwd(const HpvKernelKey& k, const HpvLaunch& l); \
+    cudaError_t hpv_dispatch_h##hp##_pts(const HpvKernelKey& k, const HpvLaunch& l);
+HPV_DECL(8)
+HPV_DECL(20)
+HPV_DECL(32)
+#undef HPV_DECL
+
+inline cudaError_t hpv_dispatch(const HpvKernelKey& k, const HpvLaunch& l) {
+#define HPV_CASE(hpv) \
+    if (k.hp == hpv) { \
+        if (l.kind == HPV_K_VARFWD) return hpv_dispatch_h##hpv##_fwd(k, l); \
+        if (l.kind == HPV_K_MLPBWD) return hpv_dispatch_h##hpv##_bwd(k, l); \
+        return hpv_dispatch_h##hpv##_pts(k, l); \
+    }
+    HPV_CASE(8)
+    HPV_CASE(20)
+    HPV_CASE(32)
+#undef HPV_CASE
+    return cudaErrorInvalidValue;
+}
+
+// mode-independent kernels (hpv_kernels_common.cu)
+cudaError_t hpv_launch_adjproj(const HpvAdjArgs& a, int grid, size_t smem, cudaStream_t s);
+cudaError_t hpv_launch_gradreduce(const HpvGradReduceArgs& a, cudaStream_t s);
+struct HpvAdamArgs {
+    const float* grad_pad;     // padded gradient (+ d eps at index theta_pad_n)
+    const int* pad_index;      // [n_theta] reference-order index -> padded index
+    int n_theta, theta_pad_n;
+    double* theta;             // [n_theta + 1] float64 master parameters, reference order, eps last
+    double* m; double* v;      // Adam moments, same layout
+    float* theta_pad;          // padded copy read by the kernels
+    float* eps;                // device scalar read by the kernels
+    double* grad_out;          // [n_theta + 1] unpadded gradient or null
+    int train_eps;
+    float lr, b1, b2, eps_hat;
+    const int* step;           // device step counter t >= 1 (incremented by the kernel when update != 0)
+    int* step_rw;
+    int update;                // 0: only unpad the gradient, 1: also apply the Adam update
+};
+cudaError_t hpv_launch_adam(const HpvAdamArgs& a, cudaStream_t s);
+cudaError_t hpv_launch_ffma_peak(float* out, int grid, int block, int iters, int variant, cudaStream_t s);

@@ -1,0 +1,245 @@
+// Fused forward kernel of the variational loss: for every element of the hp-mesh evaluate net_u and the
+// needed input derivatives at the tensor Gauss-Lobatto quadrature points, project onto the Jacobi test
+// functions by sum factorisation, subtract F_ext and reduce to the element loss and lossv.
+// Restates the graph of P2D:68-120, P1D:64-96 and ADI:108-182 (one launch instead of N_el*Nty*Ntx reduce_sum
+// sub-graphs).  See DESIGN.md "Forward kernel" for the data flow and the shared-memory plan.
+#pragma once
+#include "hpv_cta.cuh"
+
+struct HpvFwdSmem {
+    int th, xi1, tab[HPV_NTAB], G, P, red, flag, total;   // offsets in floats
+    int GS, RMAX;
+};
+
+HPV_HD int hpv_tab_mask(const HpvVarArgs& a) {
+    int m = 0;
+    for (int t = 0; t < a.n_terms; ++t) m |= (1 << a.terms[t].ltab) | (1 << a.terms[t].rtab);
+    return m;
+}
+
+HPV_HD HpvFwdSmem hpv_fwd_smem(const HpvVarArgs& a) {
+    HpvFwdSmem s;
+    int o = 0;
+    s.th = o; o += hpv_align4(a.theta_pad_n);
+    s.xi1 = o; o += hpv_align4(a.Q);
+    int m = hpv_tab_mask(a);
+    for (int t = 0; t < HPV_NTAB; ++t) {
+        s.tab[t] = -1;
+        if (m & (1 << t)) { s.tab[t] = o; o += a.Q * HPV_NP; }
+    }
+    s.GS = hpv_align4(HPV_CT * HPV_THREADS + 2 * a.Q);
+    int rmax = (HPV_CT * HPV_THREADS) / a.Q + 2;
+    s.RMAX = rmax < a.rows ? rmax : a.rows;
+    s.G = o; o += a.n_terms * s.GS;
+    s.P = o; o += a.n_terms * s.RMAX * HPV_NP;
+    s.red = o; o += 2 * HPV_THREADS;                    // doubles for the final reduction
+    s.flag = o; o += 4;
+    s.total = o;
+    return s;
+}
+
+HPV_HD float hpv_term_scale(const HpvTerm& t, float hwx, float hwy) {
+    float c = t.s;
+    if (t.px == 1) c *= hwx; else if (t.px == -1) c /= hwx;
+    if (t.py == 1) c *= hwy; else if (t.py == -1) c /= hwy;
+    return c;
+}
+
+// Cooperative copy of the launch-invariant data into shared memory (parameters, nodes, tables).
+HPV_HD void hpv_stage_common(const HpvCta& c, const HpvVarArgs& a, float* sm, int o_th, int o_xi1, const int* o_tab) {
+    for (int i = c.tid; i < a.theta_pad_n; i += c.nthreads) sm[o_th + i] = a.theta_pad[i];
+    for (int i = c.tid; i < a.Q; i += c.nthreads) sm[o_xi1 + i] = a.xi1[i];
+    for (int t = 0; t < HPV_NTAB; ++t) {
+        if (o_tab[t] < 0) continue;
+        const float* src = a.tab[t];
+        float* dst = sm + o_tab[t];
+        for (int i = c.tid * 4; i < a.Q * HPV_NP; i += c.nthreads * 4) hpv_st4(dst + i, hpv_ld4(src + i));
+    }
+}
+
+template <int DIM, int MX, int MY, int HP, int ACT>
+HPV_HD void hpv_varfwd_body(const HpvCta& c, const HpvVarArgs& a) {
+    const HpvFwdSmem L = hpv_fwd_smem(a);
+    float* sm = reinterpret_cast<float*>(c.smem);
+    float* s_th = sm + L.th;
+    float* s_xi1 = sm + L.xi1;
+    float* s_G = sm + L.G;
+    float* s_P = sm + L.P;
+    float* s_red = sm + L.red;
+    int* s_flag = reinterpret_cast<int*>(sm + L.flag);
+    const int T = c.nthreads, tid = c.tid;
+    const int Q = a.Q;
+
+    hpv_stage_common(c, a, sm, L.th, L.xi1, L.tab);
+    const float eps = a.eps[0];
+    float coef[HPV_MAX_TERMS][HPV_NFIELDS];
+    for (int t = 0; t < HPV_MAX_TERMS; ++t)
+        for (int f = 0; f < HPV_NFIELDS; ++f)
+            coef[t][f] = (t < a.n_terms) ? fmaf(eps, a.terms[t].a1[f], a.terms[t].a0[f]) : 0.0f;
+    hpv_sync(c);
+
+    const int kt = tid >> 4, rt = tid & 15;              // this thread's 4x4 tile of U (k = 4kt.., r = 4rt..)
+    float U[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) U[i][j] = 0.0f;
+
+    const int tpe = a.tiles_per_el;
+    const int npts_el = a.rows * Q;
+    int t_cur = a.cta_tile_begin[c.bid];
+    const int t_end = a.cta_tile_begin[c.bid + 1];
+
+    while (t_cur < t_end) {
+        const int e = t_cur / tpe, k0 = t_cur - e * tpe;
+        int nt = tpe - k0;
+        if (nt > HPV_CT) nt = HPV_CT;
+        if (nt > t_end - t_cur) nt = t_end - t_cur;
+        const int p0 = k0 * T;
+        int p1 = (k0 + nt) * T;
+        if (p1 > npts_el) p1 = npts_el;
+        const int ja = p0 / Q, jb = (p1 - 1) / Q, nrows = jb - ja + 1, base = ja * Q;
+        const float lox = a.el_geom[4 * e + 0], hwx = a.el_geom[4 * e + 1];
+        const float loy = a.el_geom[4 * e + 2], hwy = a.el_geom[4 * e + 3];
+
+        // (1) clear the field rows of this chunk (first/last row may be only partly covered)
+        for (int t = 0; t < a.n_terms; ++t)
+            for (int i = tid; i < nrows * Q; i += T) s_G[t * L.GS + i] = 0.0f;
+        hpv_sync(c);
+
+        // (2) network and input derivatives at the quadrature points -> projected fields
+        for (int it = 0; it < nt; ++it) {
+            const int p = p0 + it * T + tid;
+            if (p < p1) {
+                const int j = p / Q, i = p - j * Q;
+                const float x = fmaf(hwx, s_xi1[i], lox);
+                const float y = (DIM == 2) ? fmaf(hwy, s_xi1[j], loy) : 0.0f;
+                float f[HPV_NFIELDS];
+                hpv_net_point<DIM, MX, MY, HP, ACT>(s_th, a.nhid, x, y, f);
+                for (int t = 0; t < a.n_terms; ++t) {
+                    float g = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < HPV_NFIELDS; ++k) g = fmaf(coef[t][k], f[k], g);
+                    s_G[t * L.GS + (p - base)] = g;
+                }
+            }
+        }
+        hpv_sync(c);
+
+        // (3) first contraction, over the x index:  P_t[jl][r] = c_t * sum_i G_t[jl][i] * R_t[i][r]
+        {
+            const int nitems = a.n_terms * nrows * (HPV_NP / 4);
+            for (int item = tid; item < nitems; item += T) {
+                const int r4 = item & 15, rest = item >> 4;
+                const int jl = rest % nrows, t = rest / nrows;
+                const float* g = s_G + t * L.GS + jl * Q;
+                const float* R = sm + L.tab[a.terms[t].rtab] + 4 * r4;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                for (int i = 0; i < Q; ++i) {
+                    const float gv = g[i];
+                    const HpvF4 w = hpv_ld4(R + i * HPV_NP);
+                    a0 = fmaf(gv, w.x, a0); a1 = fmaf(gv, w.y, a1); a2 = fmaf(gv, w.z, a2); a3 = fmaf(gv, w.w, a3);
+                }
+                const float ct = hpv_term_scale(a.terms[t], hwx, hwy);
+                HpvF4 o; o.x = ct * a0; o.y = ct * a1; o.z = ct * a2; o.w = ct * a3;
+                hpv_st4(s_P + (t * L.RMAX + jl) * HPV_NP + 4 * r4, o);
+            }
+        }
+        hpv_sync(c);
+
+        // (4) second contraction, over the y index:  U[k][r] += sum_t sum_jl L_t[ja+jl][k] * P_t[jl][r]
+        for (int t = 0; t < a.n_terms; ++t) {
+            const float* Lt = sm + L.tab[a.terms[t].ltab] + ja * HPV_NP + 4 * kt;
+            const float* Pt = s_P + t * L.RMAX * HPV_NP + 4 * rt;
+            for (int jl = 0; jl < nrows; ++jl) {
+                const HpvF4 l4 = hpv_ld4(Lt + jl * HPV_NP), p4 = hpv_ld4(Pt + jl * HPV_NP);
+                const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, ps[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) U[i][j] = fmaf(ls[i], ps[j], U[i][j]);
+            }
+        }
+
+        t_cur += nt;
+        if (t_cur == t_end || t_cur % tpe == 0) {
+            // (5) this CTA is done with element e: publish its partial U; the last part to arrive reduces the
+            // parts in a fixed order (deterministic), forms the residual and the element loss.
+            const int nparts = a.el_nparts[e];
+            const int slot = a.el_part_off[e] + (c.bid - a.el_first_cta[e]);
+            float* up = a.Upart + (size_t)slot * HPV_NP * HPV_NP;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                HpvF4 o; o.x = U[i][0]; o.y = U[i][1]; o.z = U[i][2]; o.w = U[i][3];
+                hpv_st4(up + (4 * kt + i) * HPV_NP + 4 * rt, o);
+                U[i][0] = U[i][1] = U[i][2] = U[i][3] = 0.0f;
+            }
+            hpv_fence();
+            hpv_sync(c);
+            if (tid == 0) {
+                unsigned int prev = hpv_atomic_inc(a.el_done + e);
+                s_flag[0] = (prev == (unsigned int)(nparts - 1)) ? 1 : 0;
+            }
+            hpv_sync(c);
+            if (s_flag[0]) {
+                hpv_fence();
+                const int ntx_e = a.el_ntest[2 * e + 0], nty_e = a.el_ntest[2 * e + 1];
+                float S[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) S[i][j] = 0.0f;
+                const float* base_p = a.Upart + (size_t)a.el_part_off[e] * HPV_NP * HPV_NP;
+                for (int s = 0; s < nparts; ++s) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        HpvF4 v = hpv_ld4_cg(base_p + (size_t)s * HPV_NP * HPV_NP + (4 * kt + i) * HPV_NP + 4 * rt);
+                        S[i][0] += v.x; S[i][1] += v.y; S[i][2] += v.z; S[i][3] += v.w;
+                    }
+                }
+                float sq = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = 4 * kt + i;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = 4 * rt + j;
+                        if (k < nty_e && r < ntx_e) {
+                            const size_t idx = ((size_t)e * a.nty + k) * a.ntx + r;
+                            const float res = S[i][j] - (a.F ? a.F[idx] : 0.0f);
+                            a.Res[idx] = res;
+                            sq = fmaf(res, res, sq);
+                        } else if (k < a.nty && r < a.ntx) {
+                            a.Res[((size_t)e * a.nty + k) * a.ntx + r] = 0.0f;
+                        }
+                    }
+                }
+                const float tot = hpv_block_sum(c, s_red, sq);
+                if (tid == 0) {
+                    a.el_loss[e] = tot / (float)(ntx_e * nty_e);
+                    a.el_done[e] = 0u;
+                    hpv_fence();
+                    unsigned int prev = hpv_atomic_inc(a.n_done);
+                    s_flag[1] = (prev == (unsigned int)(a.n_el - 1)) ? 1 : 0;
+                }
+                hpv_sync(c);
+                if (s_flag[1]) {
+                    // (6) every element is finished: lossv = sum of the element losses (P2D:120), fixed order
+                    hpv_fence();
+                    double* dred = reinterpret_cast<double*>(s_red);
+                    double acc = 0.0;
+                    for (int i = tid; i < a.n_el; i += T) acc += (double)hpv_ld_cg(a.el_loss + i);
+                    dred[tid] = acc;
+                    hpv_sync(c);
+                    for (int s = T >> 1; s > 0; s >>= 1) {
+                        if (tid < s) dred[tid] += dred[tid + s];
+                        hpv_sync(c);
+                    }
+                    if (tid == 0) { a.loss[0] = dred[0]; a.n_done[0] = 0u; }
+                }
+                hpv_sync(c);
+            }
+        }
+        hpv_sync(c);
+    }
+}

@@ -55,3 +55,36 @@ def oracle_lossv(c, theta=None, eps=None):
     res = fn(Ws, bs)[1].detach().numpy()
     l, g = O.loss_and_grad(lambda W, b: fn(W, b)[0], Ws, bs)
     return l, res, g
+
+
+def engine_inputs(c, N=None):
+    """Inputs of the engine (C-ABI / emulation harness) for golden case ``c``: element corners in the
+    reference's loop order (ex outer, ey inner: P2D:69-70), 1-D nodes/weights, test tables on those nodes."""
+    kind = c["kind"]
+    out = dict(problem=kind, var_form=int(c["var_form"]), layers=c["layers"], act=ACT[kind], theta=c["theta"], eps=0.0, V=1.0)
+    if kind == "poisson1d":
+        xi = c["X_quad"].ravel(); w = c["W_quad"].ravel()
+        g = c["grid"]
+        lo, hi = g[:-1, None], g[1:, None]
+        ntx, nty = int(c["N"]), 1
+        F = np.asarray(c["F_ext"]).reshape(len(g) - 1, 1, ntx)
+    else:
+        if kind == "poisson2d":
+            xi = nodes_from_flat(c["X_quad"]); w = c["W_quad"][:len(xi), 0]
+            gx, gy = c["gridx"], c["gridy"]
+            ntx, nty = int(c["Ntx"]), int(c["Nty"])
+            F = np.asarray(c["F_ext"]).reshape(-1, nty, ntx)
+        else:
+            xi = c["T_quad"]; w = c["WT_quad"]
+            gx, gy = c["grid_x"], c["grid_t"]
+            ntx, nty = int(c["Ntx"]), int(c["Ntt"])
+            F = None
+            out["eps"] = float(c["eps0"]); out["V"] = float(c["V"])
+        lo = np.array([[gx[ex], gy[ey]] for ex in range(len(gx) - 1) for ey in range(len(gy) - 1)])
+        hi = np.array([[gx[ex + 1], gy[ey + 1]] for ex in range(len(gx) - 1) for ey in range(len(gy) - 1)])
+    Nmax = max(ntx, nty) if N is None else N
+    T = O.Test_fcn(Nmax, xi)
+    D1, D2 = O.dTest_fcn(Nmax, xi)
+    d1b, _ = O.dTest_fcn(Nmax, np.array([-1.0, 1.0]))
+    out.update(xi=xi, w=w, T=T, D1=D1, D2=D2, d1b=d1b, lo=lo, hi=hi, ntx=ntx, nty=nty, F=F)
+    return out
