@@ -48,14 +48,15 @@ def sources():
 def build(force=False, jobs=None, verbose=True):
     os.makedirs(BUILD, exist_ok=True)
     nvcc = _nvcc()
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
-    headers.append(os.path.join(ROOT, "include", "hpv.h"))
+    kernel_headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC)
+                      if f.endswith((".h", ".cuh")) and f != "hpv_host_prep.h"]
+    api_headers = kernel_headers + [os.path.join(CSRC, "hpv_host_prep.h"), os.path.join(ROOT, "include", "hpv.h")]
     todo, objs = [], []
     for src in sources():
         path = os.path.join(CSRC, src)
         obj = os.path.join(BUILD, src[:-3] + ".o")
         stamp = obj + ".sha"
-        dig = _digest(headers + [path])
+        dig = _digest((api_headers if src == "hpv_api.cu" else kernel_headers) + [path])
         objs.append(obj)
         if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:
             continue

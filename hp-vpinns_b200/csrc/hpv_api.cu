@@ -568,6 +568,13 @@ int hpv_varloss_forward(hpv_ctx* c, double* lossv, float* residual, double* el_l
     return HPV_OK;
 }
 
+int hpv_forward_async(hpv_ctx* c) {
+    if (!c) return HPV_ERR_ARG;
+    HPV_CK(cudaSetDevice(c->device));
+    { int r = ensure_ready(c); if (r) return r; }
+    return launch_forward(c);
+}
+
 static int unpad_grad(hpv_ctx* c, int update) {
     HpvAdamArgs a; memset(&a, 0, sizeof(a));
     a.grad_pad = c->redbuf.p; a.pad_index = c->pad_index.p; a.n_theta = c->net.n_theta; a.theta_pad_n = c->net.theta_pad_n;
@@ -773,19 +780,19 @@ int hpv_train_steps(hpv_ctx* c, int nsteps, double* hist) {
     { int r = need_net(c); if (r) return r; }
     if (nsteps < 0) return fail(c, HPV_ERR_ARG, "nsteps < 0");
     DevBuf<float> dh;
-    if (hist && nsteps) HPV_CK(dh.alloc(nsteps));
+    if (hist && nsteps) HPV_CK(dh.alloc((size_t)nsteps * 6));
     for (int it = 0; it < nsteps; ++it) {
         int r = hpv_loss_and_grad(c);
         if (!r && hist)
-            HPV_CK(cudaMemcpyAsync(dh.p + it, c->redbuf.p + c->loss_off, sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+            HPV_CK(cudaMemcpyAsync(dh.p + (size_t)it * 6, c->redbuf.p + c->loss_off, 6 * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
         if (!r) r = hpv_adam_step(c);
         if (r) { dh.release(); return r; }
     }
     if (hist && nsteps) {
-        std::vector<float> h(nsteps);
-        HPV_CK(cudaMemcpyAsync(h.data(), dh.p, nsteps * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        std::vector<float> h((size_t)nsteps * 6);
+        HPV_CK(cudaMemcpyAsync(h.data(), dh.p, h.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
         HPV_CK(cudaStreamSynchronize(c->stream));
-        for (int i = 0; i < nsteps; ++i) hist[i] = h[i];
+        for (size_t i = 0; i < h.size(); ++i) hist[i] = h[i];
     }
     dh.release();
     return HPV_OK;

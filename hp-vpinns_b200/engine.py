@@ -114,6 +114,9 @@ class Engine:
             out.append(el)
         return out[0] if len(out) == 1 else tuple(out)
 
+    def forward_async(self):
+        self._ck(self._lib.hpv_forward_async(self._h))
+
     def varloss_backward(self):
         g = np.zeros(self.n_params)
         ge = ctypes.c_double(0)
@@ -182,7 +185,7 @@ class Engine:
         self._ck(self._lib.hpv_reset_optimizer(self._h))
 
     def train_steps(self, nsteps, want_history=True):
-        h = np.zeros(nsteps) if want_history else None
+        h = np.zeros((nsteps, 6)) if want_history else None
         self._ck(self._lib.hpv_train_steps(self._h, int(nsteps), L.dptr(h)))
         return h
 

@@ -1,0 +1,2 @@
+"""`from hpv_b200.poisson2d import VPINN` -- the class a reference script binds in place of its own `class VPINN`."""
+from .vpinn import VPINN_Poisson2D as VPINN  # noqa: F401

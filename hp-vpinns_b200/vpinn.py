@@ -337,19 +337,9 @@ class VPINN_Poisson1D(_VPINNBase):
         raise AttributeError("'VPINN' object has no attribute 'utest_total' (as in the reference, P1D:185-195)")
 
     def train(self, nIter, tresh):
-        """P1D:201-224: Adam step; every 10 iterations read loss/lossb/lossv, record, stop below tresh; print every 100."""
-        start_time = time.time()
-        it = 0
-        while it < nIter:
-            n = min(10, nIter - it)
-            self.engine.train_steps(n, want_history=False)     # iterations it .. it+n-1
-            # the reference reads the losses right after iteration `it` (it % 10 == 0), i.e. after ONE update of
-            # this block; blocks are aligned so that the read-back happens after the first step of each block.
-            it += n
-            # (see _train_aligned below for the exact alignment)
-        self._pull()
-
-    def train(self, nIter, tresh):                               # noqa: F811  (aligned implementation)
+        """P1D:201-224: Adam step every iteration; at it % 10 == 0 read loss/lossb/lossv after that iteration's
+        update, record, stop below tresh; print every 100.  The nine updates in between run back to back on the
+        device without a read-back."""
         start_time = time.time()
         it = 0
         loss_valueb = loss_valuev = float("nan")

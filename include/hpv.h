@@ -72,6 +72,8 @@ int hpv_update_rhs_f32(hpv_ctx* ctx, const float* F_ext);
 /* lossv and the element residuals (the loop P2D:68-120 / P1D:64-96 / ADI:108-182 as one fused kernel).
  * residual [n_el][nty][ntx] fp32 and el_loss [n_el] may be NULL. */
 int hpv_varloss_forward(hpv_ctx* ctx, double* lossv, float* residual, double* el_loss);
+/* The same launch without any host read-back (stream-ordered; results stay on the device). */
+int hpv_forward_async(hpv_ctx* ctx);
 /* d lossv / d theta (reference order) and d lossv / d eps for the parameters of the last forward
  * (tf.gradients of lossv; what AdamOptimizer.minimize builds, P2D:131-132).  grad_eps may be NULL. */
 int hpv_varloss_backward(hpv_ctx* ctx, double* grad_theta, int n, double* grad_eps);
@@ -105,8 +107,8 @@ int hpv_adam_step(hpv_ctx* ctx);
 int hpv_read_losses(hpv_ctx* ctx, double* out, int n);
 int hpv_read_grad(hpv_ctx* ctx, double* grad_theta, int n, double* grad_eps);
 int hpv_reset_optimizer(hpv_ctx* ctx);
-/* nsteps full training steps (loss_and_grad + adam_step) back to back; loss_history [nsteps] (total loss
- * BEFORE each update, i.e. at the parameters the gradient was taken at) may be NULL. */
+/* nsteps full training steps (loss_and_grad + adam_step) back to back; loss_history [nsteps][6] = total, lossv
+ * and the four point losses BEFORE each update (i.e. at the parameters the gradient was taken at); may be NULL. */
 int hpv_train_steps(hpv_ctx* ctx, int nsteps, double* loss_history);
 
 /* Measurement helpers for bench.py: launch counter of this context, the dominant kernels' launch geometry,
