@@ -31,9 +31,18 @@ __global__ void __launch_bounds__(HPV_THREADS, 1) hpv_points_kernel(const __grid
     hpv_points_body<DIM, MX, MY, HP, ACT>(c, a, gbar_out);
 }
 
+// Opt in to > 48 KB of dynamic shared memory once per kernel instantiation and device (the attribute call
+// costs tens of microseconds on the host, far more than a launch).
 template <typename K>
 static cudaError_t hpv_prepare(K kernel, size_t smem) {
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static size_t prepared[16] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 15;
+    if (smem <= prepared[dev] && prepared[dev] != 0) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) prepared[dev] = smem;
+    return e;
 }
 
 template <int DIM, int MX, int MY, int HP, int ACT, int KIND>

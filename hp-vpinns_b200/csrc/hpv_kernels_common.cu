@@ -12,8 +12,15 @@ __global__ void __launch_bounds__(HPV_THREADS, 1) hpv_adjproj_kernel(const __gri
 }
 
 cudaError_t hpv_launch_adjproj(const HpvAdjArgs& a, int grid, size_t smem, cudaStream_t s) {
-    cudaError_t err = cudaFuncSetAttribute(hpv_adjproj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
+    static size_t prepared[16] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 15;
+    if (smem > prepared[dev] || prepared[dev] == 0) {
+        cudaError_t err = cudaFuncSetAttribute(hpv_adjproj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        prepared[dev] = smem;
+    }
     hpv_adjproj_kernel<<<grid, HPV_THREADS, smem, s>>>(a);
     return cudaGetLastError();
 }

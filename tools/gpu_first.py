@@ -1,7 +1,7 @@
 """Development probe for the first GPU call: parity on every golden case, FP32 probes, C3 timing."""
-import json, sys, time
+import json, os, sys, time
 import numpy as np
-sys.path.insert(0, ".")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tests import _cases as C, _gpu as G
 from oracle import hpvpinn_oracle as O
 import hpv_b200
