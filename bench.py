@@ -275,7 +275,11 @@ def run_ours(args):
     name = args.workload if args.workload != "auto" else ("c3" if world == 1 else "c4")
     wl = build_workload(name, rank, world)
     eng = make_engine(wl, local)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) torch stream carries the engine's launches, NCCL and the timing events, so
+    # that the events bracket exactly the step's work (hpv_set_stream(NULL) would mean the engine's own stream)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     eng.set_stream(stream.cuda_stream)
     ptr, nred = eng.reduce_buffer()
 

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
+#include <stdint.h>
 #include <string>
 #include <vector>
 #include "../../include/hpv.h"
@@ -56,7 +57,7 @@ struct hpv_ctx {
     DevBuf<double> master, adam_m, adam_v, grad_out;
     DevBuf<int> pad_index, step;
     // quadrature / tables
-    DevBuf<float> xi1, tab[HPV_NTAB];
+    DevBuf<float> xi1, tab[HPV_NTAB], tabN[HPV_NTAB];
     // elements
     DevBuf<float> geom, F, Res, el_loss, Upart, Gbar;
     DevBuf<int> ntest, cta_tile_begin, el_first_cta, el_part_off, el_nparts;
@@ -74,9 +75,15 @@ struct hpv_ctx {
     double lr = 1e-3, b1 = 0.9, b2 = 0.999, eps_hat = 1e-8;
     std::vector<float> host_f32;
     std::vector<double> host_f64;
+    // constant-memory mirrors of theta_pad, one per kernel translation unit kind (forward, reverse sweep, points)
+    int cslot = -1;
+    float* mirror[3] = {nullptr, nullptr, nullptr};
+    bool mirror_stale[3] = {true, true, true};
 };
 
 namespace {
+
+bool g_slot_used[16][HPV_CSLOTS];
 
 int fail(hpv_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg; else g_create_error = msg;
@@ -105,11 +112,32 @@ HpvKernelKey key_of(const hpv_ctx* c, int mx, int my) {
     return k;
 }
 
+// Bring the constant-memory copy of the parameters that kernels of `kind` read up to date (stream-ordered).
+int refresh_mirror(hpv_ctx* c, int kind) {
+    if (!c->mirror[kind]) {
+        HpvLaunch l; memset(&l, 0, sizeof(l));
+        long long out = 0;
+        l.kind = kind; l.op = 3; l.out = &out;
+        HPV_CK(hpv_dispatch(key_of(c, 0, 0), l));
+        c->mirror[kind] = reinterpret_cast<float*>((uintptr_t)out) + (size_t)c->cslot * HPV_CTHETA_MAX;
+        c->mirror_stale[kind] = true;
+    }
+    if (c->mirror_stale[kind]) {
+        HPV_CK(cudaMemcpyAsync(c->mirror[kind], c->theta_pad.p, c->net.theta_pad_n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        c->mirror_stale[kind] = false;
+    }
+    return HPV_OK;
+}
+
+void theta_changed(hpv_ctx* c) { c->mirror_stale[0] = c->mirror_stale[1] = c->mirror_stale[2] = true; }
+
 void fill_var_args(hpv_ctx* c, HpvVarArgs& a) {
     memset(&a, 0, sizeof(a));
     a.theta_pad = c->theta_pad.p; a.theta_pad_n = c->net.theta_pad_n; a.nhid = c->net.nhid; a.eps = c->eps.p;
+    a.cslot = c->cslot;
     a.Q = c->Q; a.rows = (c->net.dim == 2) ? c->Q : 1; a.xi1 = c->xi1.p;
-    for (int t = 0; t < HPV_NTAB; ++t) a.tab[t] = c->tab[t].p;
+    for (int t = 0; t < HPV_NTAB; ++t) { a.tab[t] = c->tab[t].p; a.tabN[t] = c->tabN[t].p; }
+    a.QP = hpv_align4(c->Q);
     a.n_el = c->n_el; a.el_geom = c->geom.p; a.el_ntest = c->ntest.p; a.ntx = c->ntx; a.nty = c->nty;
     a.F = c->has_F ? c->F.p : nullptr;
     a.n_terms = c->form.n_terms;
@@ -167,17 +195,22 @@ int ensure_ready(hpv_ctx* c) {
     std::vector<float> tabs[HPV_NTAB];
     hpv_build_tables(c->Q, c->N, c->w.data(), c->T.data(), c->D1.data(), c->D2.data(),
                      c->have_d1b ? c->d1b.data() : nullptr, c->form.fold_boundary, tabs);
-    for (int t = 0; t < HPV_NTAB; ++t) { int r = upload(c, c->tab[t], tabs[t]); if (r) return r; }
+    std::vector<float> nat[HPV_NTAB];
+    hpv_natural_tables(c->Q, tabs, nat);
+    for (int t = 0; t < HPV_NTAB; ++t) {
+        int r = upload(c, c->tab[t], tabs[t]); if (r) return r;
+        r = upload(c, c->tabN[t], nat[t]); if (r) return r;
+    }
     std::vector<float> xi1(c->Q);
     for (int q = 0; q < c->Q; ++q) xi1[q] = (float)(c->xi[q] + 1.0);
     { int r = upload(c, c->xi1, xi1); if (r) return r; }
 
     // forward launch plan
     HpvVarArgs a; fill_var_args(c, a);
-    const HpvFwdSmem fs = hpv_fwd_smem(a);
+    const HpvKernelKey k = key_of(c, c->form.mx, c->form.my);
+    const HpvFwdSmem fs = hpv_fwd_smem(a, hpv_slot_floats(k.dim, k.mx, k.my, k.hp, HPV_THREADS));
     c->fwd_smem = (size_t)fs.total * 4;
     if (c->fwd_smem > 227 * 1024) return fail(c, HPV_ERR_LIMIT, "forward kernel shared-memory plan exceeds 227 KB (reduce Q)");
-    const HpvKernelKey k = key_of(c, c->form.mx, c->form.my);
     {
         HpvLaunch l; memset(&l, 0, sizeof(l));
         long long out = 0;
@@ -223,6 +256,7 @@ int ensure_ready(hpv_ctx* c) {
 }
 
 int launch_forward(hpv_ctx* c) {
+    { int r = refresh_mirror(c, HPV_K_VARFWD); if (r) return r; }
     HpvVarArgs a; fill_var_args(c, a);
     HpvLaunch l; memset(&l, 0, sizeof(l));
     l.kind = HPV_K_VARFWD; l.op = 0; l.grid = c->part.n_ctas; l.block = HPV_THREADS; l.smem = c->fwd_smem;
@@ -241,6 +275,7 @@ int launch_adjproj(hpv_ctx* c) {
 }
 
 int launch_mlpbwd_var(hpv_ctx* c) {
+    { int r = refresh_mirror(c, HPV_K_MLPBWD); if (r) return r; }
     HpvBwdArgs ba; fill_var_args(c, ba.v);
     const int rows = (c->net.dim == 2) ? c->Q : 1;
     ba.Gbar = c->Gbar.p; ba.n_points = c->n_el * rows * c->Q;
@@ -264,8 +299,10 @@ int launch_gradreduce(hpv_ctx* c, int n_parts, int accumulate) {
 
 int launch_points(hpv_ctx* c, int mx, int my, int n, const float* pts, float* u, float* d1, float* d2,
                   PointSet* ps, bool want_adjoint) {
+    { int r = refresh_mirror(c, HPV_K_POINTS); if (r) return r; }
     HpvPointArgs p; memset(&p, 0, sizeof(p));
     p.theta_pad = c->theta_pad.p; p.theta_pad_n = c->net.theta_pad_n; p.nhid = c->net.nhid; p.eps = c->eps.p;
+    p.cslot = c->cslot;
     p.n = n; p.pts = pts; p.out_u = u; p.out_d1 = d1; p.out_d2 = d2;
     int grid = (n + HPV_THREADS - 1) / HPV_THREADS;
     if (grid > c->n_sm * 4) grid = c->n_sm * 4;
@@ -280,7 +317,10 @@ int launch_points(hpv_ctx* c, int mx, int my, int n, const float* pts, float* u,
     p.n_ctas = grid;
     HpvLaunch l; memset(&l, 0, sizeof(l));
     l.kind = HPV_K_POINTS; l.op = 0; l.grid = grid; l.block = HPV_THREADS;
-    l.smem = (size_t)(hpv_align4(c->net.theta_pad_n) + HPV_THREADS) * 4;
+    {
+        const HpvKernelKey kk = key_of(c, mx, my);
+        l.smem = (size_t)(HPV_THREADS + hpv_slot_floats(kk.dim, kk.mx, kk.my, kk.hp, HPV_THREADS)) * 4;
+    }
     l.stream = c->stream; l.pts = &p; l.gbar_out = gbar;
     HPV_CK(hpv_dispatch(key_of(c, mx, my), l));
     c->launches += 1;
@@ -290,9 +330,11 @@ int launch_points(hpv_ctx* c, int mx, int my, int n, const float* pts, float* u,
 int launch_mlpbwd_points(hpv_ctx* c, PointSet& ps, int& grid_out) {
     int block = 0, cps = 0; size_t smem = 0;
     { int r = plan_bwd(c, ps.mx, ps.my, block, cps, smem); if (r) return r; }
+    { int r = refresh_mirror(c, HPV_K_MLPBWD); if (r) return r; }
     HpvBwdArgs ba; memset(&ba, 0, sizeof(ba));
     HpvVarArgs& a = ba.v;
     a.theta_pad = c->theta_pad.p; a.theta_pad_n = c->net.theta_pad_n; a.nhid = c->net.nhid; a.eps = c->eps.p;
+    a.cslot = c->cslot;
     a.Q = 1; a.rows = 1; a.n_terms = 1;
     a.terms[0] = hpv_term_zero();
     for (int f = 0; f < HPV_NFIELDS; ++f) { a.terms[0].a0[f] = ps.a0[f]; a.terms[0].a1[f] = ps.a1[f]; }
@@ -369,10 +411,18 @@ int hpv_create(hpv_ctx** out, int device) {
     e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) return fail(c, HPV_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
     if (prop.major != 10) return fail(c, HPV_ERR_CUDA, "libhpv is built for sm_100a (B200) only");
+    int slot = -1;
+    for (int i = 0; i < HPV_CSLOTS; ++i) if (!g_slot_used[device & 15][i]) { slot = i; break; }
+    if (slot < 0) return fail(c, HPV_ERR_LIMIT, "too many live contexts on this device (constant-memory parameter slots: 3)");
     hpv_ctx* ctx = new hpv_ctx();
-    ctx->device = device; ctx->n_sm = prop.multiProcessorCount;
+    ctx->device = device; ctx->n_sm = prop.multiProcessorCount; ctx->cslot = slot;
+    g_slot_used[device & 15][slot] = true;
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { delete ctx; return fail(c, HPV_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
+    if (e != cudaSuccess) {
+        g_slot_used[device & 15][slot] = false;
+        delete ctx;
+        return fail(c, HPV_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    }
     ctx->stream = ctx->own_stream;
     *out = ctx;
     return HPV_OK;
@@ -384,7 +434,7 @@ void hpv_destroy(hpv_ctx* c) {
     cudaStreamSynchronize(c->stream);
     c->theta_pad.release(); c->eps.release(); c->master.release(); c->adam_m.release(); c->adam_v.release();
     c->grad_out.release(); c->pad_index.release(); c->step.release(); c->xi1.release();
-    for (int t = 0; t < HPV_NTAB; ++t) c->tab[t].release();
+    for (int t = 0; t < HPV_NTAB; ++t) { c->tab[t].release(); c->tabN[t].release(); }
     c->geom.release(); c->F.release(); c->Res.release(); c->el_loss.release(); c->Upart.release(); c->Gbar.release();
     c->ntest.release(); c->cta_tile_begin.release(); c->el_first_cta.release(); c->el_part_off.release();
     c->el_nparts.release(); c->counters.release(); c->loss.release(); c->grad_part.release(); c->redbuf.release();
@@ -393,6 +443,7 @@ void hpv_destroy(hpv_ctx* c) {
         c->ps[s].blk_loss.release();
     }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->cslot >= 0) g_slot_used[c->device & 15][c->cslot] = false;
     delete c;
 }
 
@@ -419,7 +470,10 @@ int hpv_set_network(hpv_ctx* c, int dim, const int* layers, int n_layers, int ac
     std::string err;
     HpvNet net;
     if (!hpv_net_setup(net, dim, layers, n_layers, act, err)) return fail(c, HPV_ERR_ARG, err);
+    if (net.theta_pad_n > HPV_CTHETA_MAX) return fail(c, HPV_ERR_LIMIT, "network too large for the constant-memory parameter slot (4096 padded floats)");
     c->net = net; c->have_net = true; c->ready = false;
+    c->mirror[0] = c->mirror[1] = c->mirror[2] = nullptr;
+    theta_changed(c);
     const int P = net.n_theta;
     HPV_CK(c->theta_pad.alloc(net.theta_pad_n));
     HPV_CK(cudaMemsetAsync(c->theta_pad.p, 0, net.theta_pad_n * sizeof(float), c->stream));
@@ -452,6 +506,7 @@ int hpv_set_params(hpv_ctx* c, const double* theta, int n, double eps) {
     HPV_CK(cudaMemcpyAsync(c->eps.p, pad.data() + c->net.theta_pad_n, sizeof(float), cudaMemcpyHostToDevice, c->stream));
     HPV_CK(cudaMemcpyAsync(c->master.p, m.data(), (n + 1) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     HPV_CK(cudaStreamSynchronize(c->stream));
+    theta_changed(c);
     return HPV_OK;
 }
 
@@ -584,6 +639,7 @@ static int unpad_grad(hpv_ctx* c, int update) {
     a.step = c->step.p; a.step_rw = c->step.p; a.update = update;
     HPV_CK(hpv_launch_adam(a, c->stream));
     c->launches += update ? 2 : 1;
+    if (update) theta_changed(c);
     return HPV_OK;
 }
 

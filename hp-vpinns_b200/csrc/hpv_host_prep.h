@@ -152,6 +152,17 @@ inline void hpv_build_tables(int Q, int N, const double* w, const double* T, con
     tabs[3][0] = 1.0f;
 }
 
+// Natural-layout copies [HPV_NP][QP] (QP = Q rounded up to a multiple of 4, 4 floats of tail padding) for the
+// adjoint projection, whose contractions run along the other index.
+inline void hpv_natural_tables(int Q, const std::vector<float> tabs[HPV_NTAB], std::vector<float> nat[HPV_NTAB]) {
+    const int QP = (Q + 3) & ~3;
+    for (int t = 0; t < HPV_NTAB; ++t) {
+        nat[t].assign((size_t)HPV_NP * QP + 4, 0.0f);
+        for (int q = 0; q < Q; ++q)
+            for (int n = 0; n < HPV_NP; ++n) nat[t][(size_t)n * QP + q] = tabs[t][(size_t)q * HPV_NP + n];
+    }
+}
+
 struct HpvPartition {
     int tiles_per_el = 0, n_ctas = 0, total_parts = 0;
     std::vector<int> cta_tile_begin, el_first_cta, el_part_off, el_nparts;

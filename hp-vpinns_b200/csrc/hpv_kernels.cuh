@@ -2,10 +2,11 @@
 // hpv_k_h{8,20,32}_{fwd,bwd,pts}.cu: one translation unit per padded hidden width and kernel kind, so
 // that the build parallelises (each unit instantiates 7 derivative modes x 2 activations).
 #pragma once
+#include <stdint.h>
 #include "hpv_launch.h"
 
 template <int DIM, int MX, int MY, int HP, int ACT>
-__global__ void __launch_bounds__(HPV_THREADS, 1) hpv_varfwd_kernel(const __grid_constant__ HpvVarArgs a) {
+__global__ void __launch_bounds__(HPV_THREADS, (HpvMode<DIM, MX, MY>::NCH >= 4 ? 1 : 2)) hpv_varfwd_kernel(const __grid_constant__ HpvVarArgs a) {
     extern __shared__ __align__(16) unsigned char hpv_smem[];
     HpvCta c;
     c.tid = threadIdx.x; c.nthreads = blockDim.x; c.bid = blockIdx.x; c.nblocks = gridDim.x;
@@ -32,10 +33,10 @@ __global__ void __launch_bounds__(HPV_THREADS, 1) hpv_points_kernel(const __grid
 }
 
 // Opt in to > 48 KB of dynamic shared memory once per kernel instantiation and device (the attribute call
-// costs tens of microseconds on the host, far more than a launch).
+// costs tens of microseconds on the host, far more than a launch).  `prepared` is the per-instantiation cache
+// owned by the caller (a function-local static of hpv_do, which is templated on the full kernel identity).
 template <typename K>
-static cudaError_t hpv_prepare(K kernel, size_t smem) {
-    static size_t prepared[16] = {0};
+static cudaError_t hpv_prepare(K kernel, size_t smem, size_t* prepared) {
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 15;
@@ -48,15 +49,17 @@ static cudaError_t hpv_prepare(K kernel, size_t smem) {
 template <int DIM, int MX, int MY, int HP, int ACT, int KIND>
 static cudaError_t hpv_do(const HpvLaunch& l) {
     cudaError_t err = cudaSuccess;
+    static size_t prepared[16] = {0};
     if constexpr (KIND == HPV_K_VARFWD) {
         auto k = hpv_varfwd_kernel<DIM, MX, MY, HP, ACT>;
-        if ((err = hpv_prepare(k, l.smem)) != cudaSuccess) return err;
+        if ((err = hpv_prepare(k, l.smem, prepared)) != cudaSuccess) return err;
         if (l.op == 1) {
             int n = 0;
             err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, l.block, l.smem);
             *l.out = n;
             return err;
         }
+        if (l.op == 3) { void* p = nullptr; err = cudaGetSymbolAddress(&p, hpv_c_theta); *l.out = (long long)(uintptr_t)p; return err; }
         k<<<l.grid, l.block, l.smem, l.stream>>>(*l.var);
     } else if constexpr (KIND == HPV_K_MLPBWD) {
         auto k = hpv_mlpbwd_kernel<DIM, MX, MY, HP, ACT>;
@@ -65,23 +68,25 @@ static cudaError_t hpv_do(const HpvLaunch& l) {
             *l.out = (long long)L.total * 4;
             return cudaSuccess;
         }
-        if ((err = hpv_prepare(k, l.smem)) != cudaSuccess) return err;
+        if ((err = hpv_prepare(k, l.smem, prepared)) != cudaSuccess) return err;
         if (l.op == 1) {
             int n = 0;
             err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, l.block, l.smem);
             *l.out = n;
             return err;
         }
+        if (l.op == 3) { void* p = nullptr; err = cudaGetSymbolAddress(&p, hpv_c_theta); *l.out = (long long)(uintptr_t)p; return err; }
         k<<<l.grid, l.block, l.smem, l.stream>>>(*l.bwd);
     } else {
         auto k = hpv_points_kernel<DIM, MX, MY, HP, ACT>;
-        if ((err = hpv_prepare(k, l.smem)) != cudaSuccess) return err;
+        if ((err = hpv_prepare(k, l.smem, prepared)) != cudaSuccess) return err;
         if (l.op == 1) {
             int n = 0;
             err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, l.block, l.smem);
             *l.out = n;
             return err;
         }
+        if (l.op == 3) { void* p = nullptr; err = cudaGetSymbolAddress(&p, hpv_c_theta); *l.out = (long long)(uintptr_t)p; return err; }
         k<<<l.grid, l.block, l.smem, l.stream>>>(*l.pts, l.gbar_out);
     }
     return cudaGetLastError();

@@ -6,12 +6,7 @@
 #pragma once
 #include <math.h>
 #include "hpv_types.h"
-
-#if defined(__CUDACC__)
-#define HPV_HD __host__ __device__ __forceinline__
-#else
-#define HPV_HD inline
-#endif
+#include "hpv_pair.cuh"
 
 enum { HPV_ACT_SIN = 0, HPV_ACT_TANH = 1 };
 
@@ -34,13 +29,8 @@ HPV_HD int hpv_theta_pad_n(int dim, int hp, int nhid) { return hpv_off_wo(dim, h
 // tanh as 1 - 2/(exp(2z)+1): absolute error ~1e-7 (what matters: the value feeds dot products), saturates
 // cleanly to +-1, no branches.
 HPV_HD float hpv_tanh(float z) {
-#if defined(__CUDA_ARCH__)
-    float e = exp2f(z * 2.8853900817779268f);          // exp(2z)
-    return 1.0f - __fdividef(2.0f, e + 1.0f);
-#else
-    float e = expf(2.0f * z);
-    return 1.0f - 2.0f / (e + 1.0f);
-#endif
+    const float e = hpv_ex2(z * 2.8853900817779268f);    // exp(2z): MUFU.EX2, then MUFU.RCP
+    return fmaf(-2.0f, hpv_rcp(e + 1.0f), 1.0f);
 }
 
 template <int ACT>
@@ -104,142 +94,74 @@ HPV_HD void hpv_layer1_pre(const float* th, float x, float y, HpvState<DIM, MX, 
     const float* W1 = th + hpv_off_w1();
     const float* b1 = th + hpv_off_b1(DIM, HP);
 #pragma unroll
-    for (int j4 = 0; j4 < HP / 4; ++j4) {
-        HpvF4 wx = hpv_ld4(W1 + 4 * j4), b = hpv_ld4(b1 + 4 * j4);
-        HpvF4 wy = wx;
-        if constexpr (DIM == 2) wy = hpv_ld4(W1 + HP + 4 * j4);
-        float wxs[4] = {wx.x, wx.y, wx.z, wx.w}, wys[4] = {wy.x, wy.y, wy.z, wy.w}, bs[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int j = 4 * j4 + k;
-            float zz = fmaf(x, wxs[k], bs[k]);
-            if constexpr (DIM == 2) zz = fmaf(y, wys[k], zz);
-            z.v.a[j] = zz;
-            if constexpr (M::DX) z.dx.a[j] = wxs[k];
-            if constexpr (M::DY) z.dy.a[j] = wys[k];
-            if constexpr (M::EX) z.ex.a[j] = 0.0f;
-            if constexpr (M::EY) z.ey.a[j] = 0.0f;
-        }
+    for (int j = 0; j < HP; ++j) {
+        const float wx = W1[j];
+        const float wy = (DIM == 2) ? W1[HP + j] : 0.0f;
+        float zz = fmaf(x, wx, b1[j]);
+        if constexpr (DIM == 2) zz = fmaf(y, wy, zz);
+        z.v.a[j] = zz;
+        if constexpr (M::DX) z.dx.a[j] = wx;
+        if constexpr (M::DY) z.dy.a[j] = wy;
+        if constexpr (M::EX) z.ex.a[j] = 0.0f;
+        if constexpr (M::EY) z.ey.a[j] = 0.0f;
     }
+}
+
+// tanh of a pair and its first derivative factor: a = 1 - 2/(exp(2z)+1), s1 = 1 - a^2.
+HPV_HD void hpv_tanh2(hpv_pair z, hpv_pair& a, hpv_pair& s1) {
+    const hpv_pair t = hpv_mul2(z, hpv_dup(2.8853900817779268f));
+    float t0, t1;
+    hpv_unpack(t, t0, t1);
+    const hpv_pair d = hpv_add2(hpv_pack(hpv_ex2(t0), hpv_ex2(t1)), hpv_dup(1.0f));
+    float d0, d1;
+    hpv_unpack(d, d0, d1);
+    a = hpv_fma2r(hpv_pack(hpv_rcp(d0), hpv_rcp(d1)), hpv_dup(-2.0f), hpv_dup(1.0f));
+    s1 = hpv_fma2r(hpv_mul2(a, a), hpv_dup(-1.0f), hpv_dup(1.0f));
 }
 
 // Pre-activations (z, dz, d2z) -> post-activations (h, dh, d2h), in place.
 //   h = s(z);  dh = s'(z) dz;  d2h = s''(z) dz^2 + s'(z) d2z
+// tanh runs on packed pairs of units (FMUL2/FFMA2: half the issue slots of the scalar form).
 template <int DIM, int MX, int MY, int HP, int ACT>
 HPV_HD void hpv_activate(HpvState<DIM, MX, MY, HP>& s) {
     typedef HpvMode<DIM, MX, MY> M;
+    if constexpr (ACT == HPV_ACT_TANH) {
 #pragma unroll
-    for (int j = 0; j < HP; ++j) {
-        float a, s1, s2;
-        hpv_act<ACT>(s.v.a[j], a, s1, s2);
-        s.v.a[j] = a;
-        if constexpr (M::EX) s.ex.a[j] = fmaf(s2 * s.dx.a[j], s.dx.a[j], s1 * s.ex.a[j]);
-        if constexpr (M::EY) s.ey.a[j] = fmaf(s2 * s.dy.a[j], s.dy.a[j], s1 * s.ey.a[j]);
-        if constexpr (M::DX) s.dx.a[j] = s1 * s.dx.a[j];
-        if constexpr (M::DY) s.dy.a[j] = s1 * s.dy.a[j];
-    }
-}
-
-// Hidden layer l >= 1: out = in . W + b for the value channel, out = in . W for every tangent channel.
-template <int DIM, int MX, int MY, int HP>
-HPV_HD void hpv_matmul(const float* W, const float* b, const HpvState<DIM, MX, MY, HP>& in,
-                       HpvState<DIM, MX, MY, HP>& out) {
-    typedef HpvMode<DIM, MX, MY> M;
-#pragma unroll
-    for (int j4 = 0; j4 < HP / 4; ++j4) {
-        HpvF4 bb = hpv_ld4(b + 4 * j4);
-        out.v.a[4 * j4 + 0] = bb.x; out.v.a[4 * j4 + 1] = bb.y; out.v.a[4 * j4 + 2] = bb.z; out.v.a[4 * j4 + 3] = bb.w;
-    }
-#pragma unroll
-    for (int j = 0; j < HP; ++j) {
-        if constexpr (M::DX) out.dx.a[j] = 0.0f;
-        if constexpr (M::DY) out.dy.a[j] = 0.0f;
-        if constexpr (M::EX) out.ex.a[j] = 0.0f;
-        if constexpr (M::EY) out.ey.a[j] = 0.0f;
-    }
-#pragma unroll
-    for (int i = 0; i < HP; ++i) {
-#pragma unroll
-        for (int j4 = 0; j4 < HP / 4; ++j4) {
-            HpvF4 w = hpv_ld4(W + i * HP + 4 * j4);
-            float ws[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                int j = 4 * j4 + k;
-                out.v.a[j] = fmaf(in.v.a[i], ws[k], out.v.a[j]);
-                if constexpr (M::DX) out.dx.a[j] = fmaf(in.dx.a[i], ws[k], out.dx.a[j]);
-                if constexpr (M::DY) out.dy.a[j] = fmaf(in.dy.a[i], ws[k], out.dy.a[j]);
-                if constexpr (M::EX) out.ex.a[j] = fmaf(in.ex.a[i], ws[k], out.ex.a[j]);
-                if constexpr (M::EY) out.ey.a[j] = fmaf(in.ey.a[i], ws[k], out.ey.a[j]);
+        for (int j = 0; j < HP; j += 2) {
+            hpv_pair a, s1;
+            hpv_tanh2(hpv_pack(s.v.a[j], s.v.a[j + 1]), a, s1);
+            hpv_unpack(a, s.v.a[j], s.v.a[j + 1]);
+            hpv_pair s2;
+            if constexpr (M::EX || M::EY) s2 = hpv_mul2(hpv_mul2(a, s1), hpv_dup(-2.0f));
+            if constexpr (M::DX) {
+                const hpv_pair dz = hpv_pack(s.dx.a[j], s.dx.a[j + 1]);
+                if constexpr (M::EX) {
+                    const hpv_pair e = hpv_fma2r(hpv_mul2(s2, dz), dz, hpv_mul2(s1, hpv_pack(s.ex.a[j], s.ex.a[j + 1])));
+                    hpv_unpack(e, s.ex.a[j], s.ex.a[j + 1]);
+                }
+                hpv_unpack(hpv_mul2(s1, dz), s.dx.a[j], s.dx.a[j + 1]);
+            }
+            if constexpr (M::DY) {
+                const hpv_pair dz = hpv_pack(s.dy.a[j], s.dy.a[j + 1]);
+                if constexpr (M::EY) {
+                    const hpv_pair e = hpv_fma2r(hpv_mul2(s2, dz), dz, hpv_mul2(s1, hpv_pack(s.ey.a[j], s.ey.a[j + 1])));
+                    hpv_unpack(e, s.ey.a[j], s.ey.a[j + 1]);
+                }
+                hpv_unpack(hpv_mul2(s1, dz), s.dy.a[j], s.dy.a[j + 1]);
             }
         }
-    }
-}
-
-// Transposed product for the reverse sweep: out[i] = sum_j in[j] * W[i][j]  (all channels alike, no bias).
-template <int DIM, int MX, int MY, int HP>
-HPV_HD void hpv_matmul_t(const float* W, const HpvState<DIM, MX, MY, HP>& in, HpvState<DIM, MX, MY, HP>& out) {
-    typedef HpvMode<DIM, MX, MY> M;
+    } else {
 #pragma unroll
-    for (int i = 0; i < HP; ++i) {
-        float av = 0.f, adx = 0.f, ady = 0.f, aex = 0.f, aey = 0.f;
-#pragma unroll
-        for (int j4 = 0; j4 < HP / 4; ++j4) {
-            HpvF4 w = hpv_ld4(W + i * HP + 4 * j4);
-            float ws[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                int j = 4 * j4 + k;
-                av = fmaf(in.v.a[j], ws[k], av);
-                if constexpr (M::DX) adx = fmaf(in.dx.a[j], ws[k], adx);
-                if constexpr (M::DY) ady = fmaf(in.dy.a[j], ws[k], ady);
-                if constexpr (M::EX) aex = fmaf(in.ex.a[j], ws[k], aex);
-                if constexpr (M::EY) aey = fmaf(in.ey.a[j], ws[k], aey);
-            }
-        }
-        out.v.a[i] = av;
-        if constexpr (M::DX) out.dx.a[i] = adx;
-        if constexpr (M::DY) out.dy.a[i] = ady;
-        if constexpr (M::EX) out.ex.a[i] = aex;
-        if constexpr (M::EY) out.ey.a[i] = aey;
-    }
-}
-
-// Output layer (linear): fields (u, u_x, u_y, u_xx, u_yy); absent ones are 0.
-template <int DIM, int MX, int MY, int HP>
-HPV_HD void hpv_output(const float* Wo, const HpvState<DIM, MX, MY, HP>& h, float f[HPV_NFIELDS]) {
-    typedef HpvMode<DIM, MX, MY> M;
-    float u = Wo[HP], ux = 0.f, uy = 0.f, uxx = 0.f, uyy = 0.f;
-#pragma unroll
-    for (int j4 = 0; j4 < HP / 4; ++j4) {
-        HpvF4 w = hpv_ld4(Wo + 4 * j4);
-        float ws[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int j = 4 * j4 + k;
-            u = fmaf(h.v.a[j], ws[k], u);
-            if constexpr (M::DX) ux = fmaf(h.dx.a[j], ws[k], ux);
-            if constexpr (M::DY) uy = fmaf(h.dy.a[j], ws[k], uy);
-            if constexpr (M::EX) uxx = fmaf(h.ex.a[j], ws[k], uxx);
-            if constexpr (M::EY) uyy = fmaf(h.ey.a[j], ws[k], uyy);
+        for (int j = 0; j < HP; ++j) {
+            float a, s1, s2;
+            hpv_act<ACT>(s.v.a[j], a, s1, s2);
+            s.v.a[j] = a;
+            if constexpr (M::EX) s.ex.a[j] = fmaf(s2 * s.dx.a[j], s.dx.a[j], s1 * s.ex.a[j]);
+            if constexpr (M::EY) s.ey.a[j] = fmaf(s2 * s.dy.a[j], s.dy.a[j], s1 * s.ey.a[j]);
+            if constexpr (M::DX) s.dx.a[j] = s1 * s.dx.a[j];
+            if constexpr (M::DY) s.dy.a[j] = s1 * s.dy.a[j];
         }
     }
-    f[0] = u; f[1] = ux; f[2] = uy; f[3] = uxx; f[4] = uyy;
-}
-
-// Whole network at one point.
-template <int DIM, int MX, int MY, int HP, int ACT>
-HPV_HD void hpv_net_point(const float* th, int nhid, float x, float y, float f[HPV_NFIELDS]) {
-    HpvState<DIM, MX, MY, HP> a, b;
-    hpv_layer1_pre<DIM, MX, MY, HP>(th, x, y, a);
-    hpv_activate<DIM, MX, MY, HP, ACT>(a);
-    for (int l = 1; l < nhid; ++l) {
-        const float* W = th + hpv_off_wl(DIM, HP, l);
-        hpv_matmul<DIM, MX, MY, HP>(W, W + HP * HP, a, b);
-        hpv_activate<DIM, MX, MY, HP, ACT>(b);
-        a = b;
-    }
-    hpv_output<DIM, MX, MY, HP>(th + hpv_off_wo(DIM, HP, nhid), a, f);
 }
 
 // Reverse of hpv_activate.  In: pre-activations z (value + tangents) and the adjoints of the post-activations
@@ -247,46 +169,77 @@ HPV_HD void hpv_net_point(const float* th, int nhid, float x, float y, float f[H
 //   zbar   = hbar s1 + sum_d [ dhbar_d s2 dz_d + d2hbar_d (s3 dz_d^2 + s2 d2z_d) ]
 //   dzbar  = dhbar s1 + 2 d2hbar s2 dz
 //   d2zbar = d2hbar s1
-// Also returns the post-activations in z (needed as the left factor of the weight gradient one layer up).
+// with s1, s2, s3 the first three derivatives of the activation at z (tanh: s2 = -2 a s1, s3 = -2 s1 (1 - 3 a^2)).
 template <int DIM, int MX, int MY, int HP, int ACT>
-HPV_HD void hpv_activate_bwd(HpvState<DIM, MX, MY, HP>& z, HpvState<DIM, MX, MY, HP>& g) {
+HPV_HD void hpv_activate_bwd(const HpvState<DIM, MX, MY, HP>& z, HpvState<DIM, MX, MY, HP>& g) {
     typedef HpvMode<DIM, MX, MY> M;
+    if constexpr (ACT == HPV_ACT_TANH) {
 #pragma unroll
-    for (int j = 0; j < HP; ++j) {
-        float a, s1, s2;
-        hpv_act<ACT>(z.v.a[j], a, s1, s2);
-        float zb = g.v.a[j] * s1;
-        if constexpr (M::DX) {
-            float dz = z.dx.a[j];
-            zb = fmaf(g.dx.a[j] * s2, dz, zb);
-            float dzb = g.dx.a[j] * s1;
-            if constexpr (M::EX) {
-                float s3 = hpv_act_s3<ACT>(a, s1);
-                float d2z = z.ex.a[j];
-                zb = fmaf(g.ex.a[j], fmaf(s3 * dz, dz, s2 * d2z), zb);
-                dzb = fmaf(2.0f * g.ex.a[j] * s2, dz, dzb);
-                z.ex.a[j] = fmaf(s2 * dz, dz, s1 * d2z);
-                g.ex.a[j] = g.ex.a[j] * s1;
+        for (int j = 0; j < HP; j += 2) {
+            hpv_pair a, s1;
+            hpv_tanh2(hpv_pack(z.v.a[j], z.v.a[j + 1]), a, s1);
+            hpv_pair zb = hpv_mul2(hpv_pack(g.v.a[j], g.v.a[j + 1]), s1);
+            hpv_pair s2, s3;
+            if constexpr (M::DX || M::DY) s2 = hpv_mul2(hpv_mul2(a, s1), hpv_dup(-2.0f));
+            if constexpr (M::EX || M::EY)
+                s3 = hpv_mul2(hpv_mul2(s1, hpv_fma2r(hpv_mul2(a, a), hpv_dup(-3.0f), hpv_dup(1.0f))), hpv_dup(-2.0f));
+            if constexpr (M::DX) {
+                const hpv_pair dz = hpv_pack(z.dx.a[j], z.dx.a[j + 1]), gd = hpv_pack(g.dx.a[j], g.dx.a[j + 1]);
+                zb = hpv_fma2r(hpv_mul2(gd, s2), dz, zb);
+                hpv_pair dzb = hpv_mul2(gd, s1);
+                if constexpr (M::EX) {
+                    const hpv_pair d2z = hpv_pack(z.ex.a[j], z.ex.a[j + 1]), ge = hpv_pack(g.ex.a[j], g.ex.a[j + 1]);
+                    zb = hpv_fma2r(ge, hpv_fma2r(hpv_mul2(s3, dz), dz, hpv_mul2(s2, d2z)), zb);
+                    dzb = hpv_fma2r(hpv_mul2(hpv_mul2(ge, s2), hpv_dup(2.0f)), dz, dzb);
+                    hpv_unpack(hpv_mul2(ge, s1), g.ex.a[j], g.ex.a[j + 1]);
+                }
+                hpv_unpack(dzb, g.dx.a[j], g.dx.a[j + 1]);
             }
-            z.dx.a[j] = s1 * dz;
-            g.dx.a[j] = dzb;
-        }
-        if constexpr (M::DY) {
-            float dz = z.dy.a[j];
-            zb = fmaf(g.dy.a[j] * s2, dz, zb);
-            float dzb = g.dy.a[j] * s1;
-            if constexpr (M::EY) {
-                float s3 = hpv_act_s3<ACT>(a, s1);
-                float d2z = z.ey.a[j];
-                zb = fmaf(g.ey.a[j], fmaf(s3 * dz, dz, s2 * d2z), zb);
-                dzb = fmaf(2.0f * g.ey.a[j] * s2, dz, dzb);
-                z.ey.a[j] = fmaf(s2 * dz, dz, s1 * d2z);
-                g.ey.a[j] = g.ey.a[j] * s1;
+            if constexpr (M::DY) {
+                const hpv_pair dz = hpv_pack(z.dy.a[j], z.dy.a[j + 1]), gd = hpv_pack(g.dy.a[j], g.dy.a[j + 1]);
+                zb = hpv_fma2r(hpv_mul2(gd, s2), dz, zb);
+                hpv_pair dzb = hpv_mul2(gd, s1);
+                if constexpr (M::EY) {
+                    const hpv_pair d2z = hpv_pack(z.ey.a[j], z.ey.a[j + 1]), ge = hpv_pack(g.ey.a[j], g.ey.a[j + 1]);
+                    zb = hpv_fma2r(ge, hpv_fma2r(hpv_mul2(s3, dz), dz, hpv_mul2(s2, d2z)), zb);
+                    dzb = hpv_fma2r(hpv_mul2(hpv_mul2(ge, s2), hpv_dup(2.0f)), dz, dzb);
+                    hpv_unpack(hpv_mul2(ge, s1), g.ey.a[j], g.ey.a[j + 1]);
+                }
+                hpv_unpack(dzb, g.dy.a[j], g.dy.a[j + 1]);
             }
-            z.dy.a[j] = s1 * dz;
-            g.dy.a[j] = dzb;
+            hpv_unpack(zb, g.v.a[j], g.v.a[j + 1]);
         }
-        z.v.a[j] = a;
-        g.v.a[j] = zb;
+    } else {
+#pragma unroll
+        for (int j = 0; j < HP; ++j) {
+            float a, s1, s2;
+            hpv_act<ACT>(z.v.a[j], a, s1, s2);
+            float zb = g.v.a[j] * s1;
+            if constexpr (M::DX) {
+                const float dz = z.dx.a[j];
+                zb = fmaf(g.dx.a[j] * s2, dz, zb);
+                float dzb = g.dx.a[j] * s1;
+                if constexpr (M::EX) {
+                    const float s3 = hpv_act_s3<ACT>(a, s1), d2z = z.ex.a[j];
+                    zb = fmaf(g.ex.a[j], fmaf(s3 * dz, dz, s2 * d2z), zb);
+                    dzb = fmaf(2.0f * g.ex.a[j] * s2, dz, dzb);
+                    g.ex.a[j] = g.ex.a[j] * s1;
+                }
+                g.dx.a[j] = dzb;
+            }
+            if constexpr (M::DY) {
+                const float dz = z.dy.a[j];
+                zb = fmaf(g.dy.a[j] * s2, dz, zb);
+                float dzb = g.dy.a[j] * s1;
+                if constexpr (M::EY) {
+                    const float s3 = hpv_act_s3<ACT>(a, s1), d2z = z.ey.a[j];
+                    zb = fmaf(g.ey.a[j], fmaf(s3 * dz, dz, s2 * d2z), zb);
+                    dzb = fmaf(2.0f * g.ey.a[j] * s2, dz, dzb);
+                    g.ey.a[j] = g.ey.a[j] * s1;
+                }
+                g.dy.a[j] = dzb;
+            }
+            g.v.a[j] = zb;
+        }
     }
 }

@@ -5,14 +5,17 @@
 // per-CTA partial sums of r_i^2.
 #pragma once
 #include "hpv_cta.cuh"
+#include "hpv_const.cuh"
+#include "hpv_slot.cuh"
 
 template <int DIM, int MX, int MY, int HP, int ACT>
 HPV_HD void hpv_points_body(const HpvCta& c, const HpvPointArgs& a, float* gbar_out) {
+    // shared memory: [reduction scratch: T floats][activation slot: NCH*T*SP floats]
     float* sm = reinterpret_cast<float*>(c.smem);
-    float* s_th = sm;
-    float* s_red = sm + hpv_align4(a.theta_pad_n);
+    float* s_red = sm;
     const int T = c.nthreads, tid = c.tid;
-    for (int i = tid; i < a.theta_pad_n; i += T) s_th[i] = a.theta_pad[i];
+    float* s_slot = sm + T;
+    const float* th = HPV_THETA(a.theta_pad, a.cslot);
     const float eps = a.eps[0];
     float cf[HPV_NFIELDS];
     for (int k = 0; k < HPV_NFIELDS; ++k) cf[k] = fmaf(eps, a.a1[k], a.a0[k]);
@@ -24,7 +27,7 @@ HPV_HD void hpv_points_body(const HpvCta& c, const HpvPointArgs& a, float* gbar_
             const float x = a.pts[(size_t)i * DIM];
             const float y = (DIM == 2) ? a.pts[(size_t)i * DIM + 1] : 0.0f;
             float f[HPV_NFIELDS];
-            hpv_net_point<DIM, MX, MY, HP, ACT>(s_th, a.nhid, x, y, f);
+            hpv_net_point_slot<DIM, MX, MY, HP, ACT>(th, a.nhid, x, y, s_slot, T, tid, f);
             if (a.out_u) a.out_u[i] = f[0];
             if (a.out_d1) { a.out_d1[(size_t)i * DIM] = f[1]; if (DIM == 2) a.out_d1[(size_t)i * DIM + 1] = f[2]; }
             if (a.out_d2) { a.out_d2[(size_t)i * DIM] = f[3]; if (DIM == 2) a.out_d2[(size_t)i * DIM + 1] = f[4]; }

@@ -1,0 +1,193 @@
+// Layer products of the MLP with the weights read from constant memory through the uniform datapath (see
+// hpv_const.cuh), the activations of a point kept in a per-thread row of shared memory
+// ("slot": [channel][thread][unit], unit contiguous, row stride SP chosen so that 128-bit accesses of a warp
+// are bank-conflict free) and the accumulation done with packed FP32x2 fused multiply-adds (fma.rn.f32x2,
+// SASS FFMA2): one issue slot per two FMAs, which leaves the other issue slot of the FMA pipe's two-cycle
+// occupancy to the loads, the activation arithmetic and the loop control.  The loops over the input units are
+// rolled (4 units per trip), so the hot code stays a few KB and resident in the instruction cache -- the fully
+// unrolled register-resident form of hpv_math.cuh stalls on instruction fetch (profiles/r01a_*).
+#pragma once
+#include "hpv_math.cuh"
+
+template <int HP> struct HpvSP { static constexpr int value = ((HP / 4) % 2 == 1) ? HP : HP + 4; };
+HPV_HD int hpv_sp(int hp) { return ((hp / 4) % 2 == 1) ? hp : hp + 4; }
+// channels of a (canonical) derivative mode: value + one per carried first / second derivative
+HPV_HD int hpv_mode_nch(int dim, int mx, int my) {
+    int n = 1 + (mx >= 1 ? 1 : 0) + (mx >= 2 ? 1 : 0);
+    if (dim == 2) n += (my >= 1 ? 1 : 0) + (my >= 2 ? 1 : 0);
+    return n;
+}
+HPV_HD int hpv_slot_floats(int dim, int mx, int my, int hp, int T) { return hpv_mode_nch(dim, mx, my) * T * hpv_sp(hp); }
+
+// Visit the channels a mode carries: f(array of HP floats, channel slot index).
+template <class M, class S, class F>
+HPV_HD void hpv_each_ch(S& s, F f) {
+    f(s.v.a, M::C_V);
+    if constexpr (M::DX) f(s.dx.a, M::C_DX);
+    if constexpr (M::DY) f(s.dy.a, M::C_DY);
+    if constexpr (M::EX) f(s.ex.a, M::C_EX);
+    if constexpr (M::EY) f(s.ey.a, M::C_EY);
+}
+
+template <int DIM, int MX, int MY, int HP>
+HPV_HD void hpv_store_state(float* slot, int T, int tid, const HpvState<DIM, MX, MY, HP>& s) {
+    typedef HpvMode<DIM, MX, MY> M;
+    constexpr int SP = HpvSP<HP>::value;
+    hpv_each_ch<M>(s, [&](const float* a, int c) {
+        float* row = slot + ((size_t)c * T + tid) * SP;
+#pragma unroll
+        for (int j4 = 0; j4 < HP / 4; ++j4) {
+            HpvF4 o; o.x = a[4 * j4]; o.y = a[4 * j4 + 1]; o.z = a[4 * j4 + 2]; o.w = a[4 * j4 + 3];
+            hpv_st4(row + 4 * j4, o);
+        }
+    });
+}
+
+template <int DIM, int MX, int MY, int HP>
+HPV_HD void hpv_load_state(const float* slot, int T, int tid, HpvState<DIM, MX, MY, HP>& s) {
+    typedef HpvMode<DIM, MX, MY> M;
+    constexpr int SP = HpvSP<HP>::value;
+    hpv_each_ch<M>(s, [&](float* a, int c) {
+        const float* row = slot + ((size_t)c * T + tid) * SP;
+#pragma unroll
+        for (int j4 = 0; j4 < HP / 4; ++j4) {
+            const HpvF4 o = hpv_ld4(row + 4 * j4);
+            a[4 * j4] = o.x; a[4 * j4 + 1] = o.y; a[4 * j4 + 2] = o.z; a[4 * j4 + 3] = o.w;
+        }
+    });
+}
+
+// out = in . W (+ b on the value channel), inputs read from this thread's slot rows, outputs in registers.
+template <int DIM, int MX, int MY, int HP>
+HPV_HD void hpv_matmul_slot(const float* W, const float* b, const float* slot, int T, int tid,
+                            HpvState<DIM, MX, MY, HP>& out) {
+    typedef HpvMode<DIM, MX, MY> M;
+    constexpr int SP = HpvSP<HP>::value, NCH = M::NCH;
+    hpv_pair acc[NCH][HP / 2];
+#pragma unroll
+    for (int j4 = 0; j4 < HP / 4; ++j4) {
+        acc[0][2 * j4] = hpv_pack(b[4 * j4], b[4 * j4 + 1]);
+        acc[0][2 * j4 + 1] = hpv_pack(b[4 * j4 + 2], b[4 * j4 + 3]);
+#pragma unroll
+        for (int c = 1; c < NCH; ++c) { acc[c][2 * j4] = hpv_pack(0.0f, 0.0f); acc[c][2 * j4 + 1] = hpv_pack(0.0f, 0.0f); }
+    }
+    const float* row = slot + (size_t)tid * SP;
+#pragma unroll 1
+    for (int i4 = 0; i4 < HP / 4; ++i4) {
+        float x[NCH][4];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const HpvF4 v = hpv_ld4(row + (size_t)c * T * SP + 4 * i4);
+            x[c][0] = v.x; x[c][1] = v.y; x[c][2] = v.z; x[c][3] = v.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float* wr = W + (4 * i4 + k) * HP;
+            hpv_pair xd[NCH];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) xd[c] = hpv_pack(x[c][k], x[c][k]);
+#pragma unroll
+            for (int j4 = 0; j4 < HP / 4; ++j4) {
+                const hpv_pair w0 = hpv_pack(wr[4 * j4], wr[4 * j4 + 1]), w1 = hpv_pack(wr[4 * j4 + 2], wr[4 * j4 + 3]);
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    hpv_fma2(acc[c][2 * j4], xd[c], w0);
+                    hpv_fma2(acc[c][2 * j4 + 1], xd[c], w1);
+                }
+            }
+        }
+    }
+    hpv_each_ch<M>(out, [&](float* a, int c) {
+#pragma unroll
+        for (int j2 = 0; j2 < HP / 2; ++j2) hpv_unpack(acc[c][j2], a[2 * j2], a[2 * j2 + 1]);
+    });
+}
+
+// Transposed product of the reverse sweep: out[i] = sum_j in[j] W[i][j] for every channel; inputs in registers,
+// outputs written to this thread's slot rows (which may be the rows the inputs were loaded from).
+template <int DIM, int MX, int MY, int HP>
+HPV_HD void hpv_matmul_t_slot(const float* W, const HpvState<DIM, MX, MY, HP>& in, float* slot, int T, int tid) {
+    typedef HpvMode<DIM, MX, MY> M;
+    constexpr int SP = HpvSP<HP>::value, NCH = M::NCH;
+    hpv_pair inp[NCH][HP / 2];
+    hpv_each_ch<M>(in, [&](const float* a, int c) {
+#pragma unroll
+        for (int j2 = 0; j2 < HP / 2; ++j2) inp[c][j2] = hpv_pack(a[2 * j2], a[2 * j2 + 1]);
+    });
+    float* row = slot + (size_t)tid * SP;
+#pragma unroll 1
+    for (int i4 = 0; i4 < HP / 4; ++i4) {
+        float o[NCH][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float* wr = W + (4 * i4 + k) * HP;
+            hpv_pair s[NCH];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) s[c] = hpv_pack(0.0f, 0.0f);
+#pragma unroll
+            for (int j4 = 0; j4 < HP / 4; ++j4) {
+                const hpv_pair w0 = hpv_pack(wr[4 * j4], wr[4 * j4 + 1]), w1 = hpv_pack(wr[4 * j4 + 2], wr[4 * j4 + 3]);
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    hpv_fma2(s[c], inp[c][2 * j4], w0);
+                    hpv_fma2(s[c], inp[c][2 * j4 + 1], w1);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                float lo, hi;
+                hpv_unpack(s[c], lo, hi);
+                o[c][k] = lo + hi;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            HpvF4 v; v.x = o[c][0]; v.y = o[c][1]; v.z = o[c][2]; v.w = o[c][3];
+            hpv_st4(row + (size_t)c * T * SP + 4 * i4, v);
+        }
+    }
+}
+
+// Output layer from the slot: fields (u, u_x, u_y, u_xx, u_yy); absent ones are 0.
+template <int DIM, int MX, int MY, int HP>
+HPV_HD void hpv_output_slot(const float* Wo, const float* slot, int T, int tid, float f[HPV_NFIELDS]) {
+    typedef HpvMode<DIM, MX, MY> M;
+    constexpr int SP = HpvSP<HP>::value, NCH = M::NCH;
+    float acc[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) acc[c] = 0.0f;
+    const float* row = slot + (size_t)tid * SP;
+#pragma unroll 1
+    for (int i4 = 0; i4 < HP / 4; ++i4) {
+        const float w0 = Wo[4 * i4], w1 = Wo[4 * i4 + 1], w2 = Wo[4 * i4 + 2], w3 = Wo[4 * i4 + 3];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const HpvF4 v = hpv_ld4(row + (size_t)c * T * SP + 4 * i4);
+            acc[c] = fmaf(v.x, w0, acc[c]); acc[c] = fmaf(v.y, w1, acc[c]);
+            acc[c] = fmaf(v.z, w2, acc[c]); acc[c] = fmaf(v.w, w3, acc[c]);
+        }
+    }
+    f[0] = acc[M::C_V] + Wo[HP];
+    f[1] = M::DX ? acc[M::DX ? M::C_DX : 0] : 0.0f;
+    f[2] = M::DY ? acc[M::DY ? M::C_DY : 0] : 0.0f;
+    f[3] = M::EX ? acc[M::EX ? M::C_EX : 0] : 0.0f;
+    f[4] = M::EY ? acc[M::EY ? M::C_EY : 0] : 0.0f;
+}
+
+// Whole network at one point through a slot (the forward kernel's inner loop).
+template <int DIM, int MX, int MY, int HP, int ACT>
+HPV_HD void hpv_net_point_slot(const float* th, int nhid, float x, float y, float* slot, int T, int tid,
+                               float f[HPV_NFIELDS]) {
+    HpvState<DIM, MX, MY, HP> s;
+    hpv_layer1_pre<DIM, MX, MY, HP>(th, x, y, s);
+    hpv_activate<DIM, MX, MY, HP, ACT>(s);
+    hpv_store_state<DIM, MX, MY, HP>(slot, T, tid, s);
+#pragma unroll 1
+    for (int l = 1; l < nhid; ++l) {
+        const float* W = th + hpv_off_wl(DIM, HP, l);
+        hpv_matmul_slot<DIM, MX, MY, HP>(W, W + HP * HP, slot, T, tid, s);
+        hpv_activate<DIM, MX, MY, HP, ACT>(s);
+        hpv_store_state<DIM, MX, MY, HP>(slot, T, tid, s);
+    }
+    hpv_output_slot<DIM, MX, MY, HP>(th + hpv_off_wo(DIM, HP, nhid), slot, T, tid, f);
+}

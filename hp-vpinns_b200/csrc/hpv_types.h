@@ -11,6 +11,8 @@
 #define HPV_MAX_HIDDEN 8       // hidden layers
 #define HPV_QMAX 128           // quadrature points per direction
 #define HPV_NTAB 4             // T*w, D1*w, D2*w, ONE
+#define HPV_CSLOTS 3            // contexts per device whose parameters can be resident in constant memory
+#define HPV_CTHETA_MAX 4096     // floats of padded parameters per context (16 KB)
 
 // One projected term:  U += s * Jx^px * Jy^py * (L-table) . G . (R-table)^T,
 // with the point field  G = sum_f (a0[f] + eps*a1[f]) * field_f  (field order above).
@@ -25,8 +27,9 @@ struct HpvTerm {
 // Arguments of the fused variational kernels (forward: residual + loss; backward: d loss / d theta, d eps).
 struct HpvVarArgs {
     // network (padded layout, see hpv_host_prep.h)
-    const float* theta_pad;
+    const float* theta_pad;    // global copy (host emulation; on the device the kernels read constant slot `cslot`)
     int theta_pad_n;
+    int cslot;
     int nhid;                  // number of hidden layers
     const float* eps;          // device scalar (AdvDiff diffusivity), never null
     // quadrature and test-function tables
@@ -34,6 +37,8 @@ struct HpvVarArgs {
     int rows;                  // rows per element: Q in 2-D, 1 in 1-D
     const float* xi1;          // [Q] xi + 1
     const float* tab[HPV_NTAB];// transposed weighted tables [Q][HPV_NP]
+    const float* tabN[HPV_NTAB];// the same tables in natural layout [HPV_NP][QP] (+4 floats of padding), QP = align4(Q)
+    int QP;
     // elements
     int n_el;
     const float* el_geom;      // [n_el][4] lo_x, halfwidth_x, lo_y, halfwidth_y
@@ -69,6 +74,7 @@ struct HpvVarArgs {
 struct HpvPointArgs {
     const float* theta_pad;
     int theta_pad_n;
+    int cslot;
     int nhid;
     const float* eps;
     int n;

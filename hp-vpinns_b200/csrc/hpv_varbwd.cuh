@@ -7,8 +7,10 @@
 // A third, tiny kernel (hpv_gradreduce_body) sums the per-CTA partial gradients in a fixed order.
 #pragma once
 #include "hpv_varfwd.cuh"
+#include "hpv_slot.cuh"
 
 #define HPV_ADJ_RS 16          // rows of an element handled by one CTA of K1
+#define HPV_ADJ_RSP 20         // padded row count (stride of the transposed V buffer, conflict-free for 128-bit loads)
 
 struct HpvAdjSmem { int tab[HPV_NTAB], Rbar, V, total; };
 
@@ -18,10 +20,10 @@ HPV_HD HpvAdjSmem hpv_adj_smem(const HpvVarArgs& a) {
     int m = hpv_tab_mask(a);
     for (int t = 0; t < HPV_NTAB; ++t) {
         s.tab[t] = -1;
-        if (m & (1 << t)) { s.tab[t] = o; o += a.Q * HPV_NP; }
+        if (m & (1 << t)) { s.tab[t] = o; o += HPV_NP * a.QP + 4; }
     }
     s.Rbar = o; o += HPV_NP * HPV_NP;
-    s.V = o; o += a.n_terms * HPV_ADJ_RS * HPV_NP;
+    s.V = o; o += a.n_terms * HPV_NP * HPV_ADJ_RSP;
     s.total = o;
     return s;
 }
@@ -33,13 +35,15 @@ struct HpvAdjArgs {
     int slabs_per_el;
 };
 
+// One CTA per (element, slab of HPV_ADJ_RS rows).  Both contractions are register-tiled 4x4 with 128-bit
+// shared-memory loads along the contiguous index of the natural-layout tables.
 HPV_HD void hpv_adjproj_body(const HpvCta& c, const HpvAdjArgs& aa) {
     const HpvVarArgs& a = aa.v;
     const HpvAdjSmem L = hpv_adj_smem(a);
     float* sm = reinterpret_cast<float*>(c.smem);
     float* s_R = sm + L.Rbar;
     float* s_V = sm + L.V;
-    const int T = c.nthreads, tid = c.tid, Q = a.Q;
+    const int T = c.nthreads, tid = c.tid, Q = a.Q, QP = a.QP;
     const int e = c.bid / aa.slabs_per_el, slab = c.bid - e * aa.slabs_per_el;
     const int j0 = slab * HPV_ADJ_RS;
     int nrows = a.rows - j0;
@@ -48,9 +52,9 @@ HPV_HD void hpv_adjproj_body(const HpvCta& c, const HpvAdjArgs& aa) {
 
     for (int t = 0; t < HPV_NTAB; ++t) {
         if (L.tab[t] < 0) continue;
-        const float* src = a.tab[t];
+        const float* src = a.tabN[t];
         float* dst = sm + L.tab[t];
-        for (int i = tid * 4; i < Q * HPV_NP; i += T * 4) hpv_st4(dst + i, hpv_ld4(src + i));
+        for (int i = tid * 4; i < HPV_NP * QP + 4; i += T * 4) hpv_st4(dst + i, hpv_ld4(src + i));
     }
     const int ntx_e = a.el_ntest[2 * e + 0], nty_e = a.el_ntest[2 * e + 1];
     const float rs = a.loss_scale * 2.0f / (float)(ntx_e * nty_e);
@@ -62,41 +66,71 @@ HPV_HD void hpv_adjproj_body(const HpvCta& c, const HpvAdjArgs& aa) {
     }
     hpv_sync(c);
 
-    // V_t[jl][r] = sum_k L_t[j0+jl][k] * Rbar[k][r]
+    // V_t[r][jl] = sum_k L_t[k][j0+jl] * Rbar[k][r]      (tile: 4 jl x 4 r)
     {
-        const int nitems = a.n_terms * nrows * (HPV_NP / 4);
-        for (int item = tid; item < nitems; item += T) {
-            const int r4 = item & 15, rest = item >> 4;
-            const int jl = rest % nrows, t = rest / nrows;
-            const float* Lt = sm + L.tab[a.terms[t].ltab] + (j0 + jl) * HPV_NP;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const int njl4 = (nrows + 3) >> 2;
+        const int ntiles = a.n_terms * njl4 * (HPV_NP / 4);
+        for (int tile = tid; tile < ntiles; tile += T) {
+            const int r4 = tile & 15, rest = tile >> 4;
+            const int jl4 = rest % njl4, t = rest / njl4;
+            const float* Lt = sm + L.tab[a.terms[t].ltab] + j0 + 4 * jl4;
+            float acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
             for (int k = 0; k < nty_e; ++k) {
-                const float lv = Lt[k];
-                const HpvF4 w = hpv_ld4(s_R + k * HPV_NP + 4 * r4);
-                a0 = fmaf(lv, w.x, a0); a1 = fmaf(lv, w.y, a1); a2 = fmaf(lv, w.z, a2); a3 = fmaf(lv, w.w, a3);
+                const HpvF4 l4 = hpv_ld4(Lt + k * QP), b4 = hpv_ld4(s_R + k * HPV_NP + 4 * r4);
+                const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ls[i], bs[j], acc[i][j]);
             }
-            HpvF4 o; o.x = a0; o.y = a1; o.z = a2; o.w = a3;
-            hpv_st4(s_V + (t * HPV_ADJ_RS + jl) * HPV_NP + 4 * r4, o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                HpvF4 o; o.x = acc[0][j]; o.y = acc[1][j]; o.z = acc[2][j]; o.w = acc[3][j];
+                hpv_st4(s_V + (t * HPV_NP + 4 * r4 + j) * HPV_ADJ_RSP + 4 * jl4, o);
+            }
         }
     }
     hpv_sync(c);
 
-    // Gbar_t[j][i] = c_t * sum_r V_t[jl][r] * R_t[i][r]
+    // Gbar_t[j0+jl][i] = c_t * sum_r V_t[r][jl] * R_t[r][i]      (tile: 4 jl x 4 i)
     {
         const float hwx = a.el_geom[4 * e + 1], hwy = a.el_geom[4 * e + 3];
-        const int nitems = a.n_terms * nrows * Q;
-        for (int item = tid; item < nitems; item += T) {
-            const int i = item % Q, rest = item / Q;
-            const int jl = rest % nrows, t = rest / nrows;
-            const float* Vt = s_V + (t * HPV_ADJ_RS + jl) * HPV_NP;
-            const float* R = sm + L.tab[a.terms[t].rtab] + i * HPV_NP;
-            float acc = 0.0f;
-            for (int r4 = 0; r4 < HPV_NP / 4; ++r4) {
-                const HpvF4 v = hpv_ld4(Vt + 4 * r4), w = hpv_ld4(R + 4 * r4);
-                acc = fmaf(v.x, w.x, acc); acc = fmaf(v.y, w.y, acc); acc = fmaf(v.z, w.z, acc); acc = fmaf(v.w, w.w, acc);
+        const int njl4 = (nrows + 3) >> 2, ni4 = QP >> 2;
+        const int ntiles = a.n_terms * njl4 * ni4;
+        for (int tile = tid; tile < ntiles; tile += T) {
+            const int i4 = tile % ni4, rest = tile / ni4;
+            const int jl4 = rest % njl4, t = rest / njl4;
+            const float* Vt = s_V + (size_t)t * HPV_NP * HPV_ADJ_RSP + 4 * jl4;
+            const float* R = sm + L.tab[a.terms[t].rtab] + 4 * i4;
+            float acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+            for (int r = 0; r < ntx_e; ++r) {
+                const HpvF4 v4 = hpv_ld4(Vt + r * HPV_ADJ_RSP), w4 = hpv_ld4(R + r * QP);
+                const float vs[4] = {v4.x, v4.y, v4.z, v4.w}, ws[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(vs[i], ws[j], acc[i][j]);
             }
             const float ct = hpv_term_scale(a.terms[t], hwx, hwy);
-            aa.Gbar[((size_t)t * a.n_el + e) * npts_el + (j0 + jl) * Q + i] = ct * acc;
+            float* out = aa.Gbar + ((size_t)t * a.n_el + e) * npts_el;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int jl = 4 * jl4 + i;
+                if (jl >= nrows) continue;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int ii = 4 * i4 + j;
+                    if (ii < Q) out[(j0 + jl) * Q + ii] = ct * acc[i][j];
+                }
+            }
         }
     }
 }
@@ -104,8 +138,6 @@ HPV_HD void hpv_adjproj_body(const HpvCta& c, const HpvAdjArgs& aa) {
 // ---------------------------------------------------------------------------------------------------------
 // K2: reverse sweep through the MLP.
 // ---------------------------------------------------------------------------------------------------------
-template <int HP> struct HpvSP { static constexpr int value = ((HP / 4) % 2 == 1) ? HP : HP + 4; };
-
 struct HpvBwdArgs {
     HpvVarArgs v;
     const float* Gbar;         // [term][n_points]  (n_points = n_el*rows*Q for the variational loss)
@@ -119,145 +151,106 @@ template <int DIM, int MX, int MY, int HP>
 struct HpvBwdSmem {
     typedef HpvMode<DIM, MX, MY> M;
     static constexpr int SP = HpvSP<HP>::value;
-    int th, gw, slots, in0, go, scratch, red, total, NS, slot_sz;
+    int gw, slots, in0, go, scratch, red, total, NS, slot_sz;
     HPV_HD HpvBwdSmem(int theta_pad_n, int nhid, int T) {
         int o = 0;
-        th = o; o += hpv_align4(theta_pad_n);
         gw = o; o += hpv_align4(theta_pad_n);
         NS = nhid - 1 > 2 ? nhid - 1 : 2;
         slot_sz = M::NCH * T * SP;
         slots = o; o += NS * slot_sz;
         in0 = o; o += 3 * T * 4;
         go = o; o += M::NCH * T * 4;
-        scratch = o; o += T * 16;
+        scratch = o; o += T * 32;
         red = o; o += T;
         total = o;
     }
 };
 
-template <int DIM, int MX, int MY, int HP>
-HPV_HD void hpv_store_state(float* slot, int T, int tid, const HpvState<DIM, MX, MY, HP>& s) {
-    typedef HpvMode<DIM, MX, MY> M;
-    constexpr int SP = HpvSP<HP>::value;
-#pragma unroll
-    for (int j4 = 0; j4 < HP / 4; ++j4) {
-        HpvF4 o;
-        o.x = s.v.a[4 * j4]; o.y = s.v.a[4 * j4 + 1]; o.z = s.v.a[4 * j4 + 2]; o.w = s.v.a[4 * j4 + 3];
-        hpv_st4(slot + (M::C_V * T + tid) * SP + 4 * j4, o);
-        if constexpr (M::DX) {
-            o.x = s.dx.a[4 * j4]; o.y = s.dx.a[4 * j4 + 1]; o.z = s.dx.a[4 * j4 + 2]; o.w = s.dx.a[4 * j4 + 3];
-            hpv_st4(slot + (M::C_DX * T + tid) * SP + 4 * j4, o);
-        }
-        if constexpr (M::DY) {
-            o.x = s.dy.a[4 * j4]; o.y = s.dy.a[4 * j4 + 1]; o.z = s.dy.a[4 * j4 + 2]; o.w = s.dy.a[4 * j4 + 3];
-            hpv_st4(slot + (M::C_DY * T + tid) * SP + 4 * j4, o);
-        }
-        if constexpr (M::EX) {
-            o.x = s.ex.a[4 * j4]; o.y = s.ex.a[4 * j4 + 1]; o.z = s.ex.a[4 * j4 + 2]; o.w = s.ex.a[4 * j4 + 3];
-            hpv_st4(slot + (M::C_EX * T + tid) * SP + 4 * j4, o);
-        }
-        if constexpr (M::EY) {
-            o.x = s.ey.a[4 * j4]; o.y = s.ey.a[4 * j4 + 1]; o.z = s.ey.a[4 * j4 + 2]; o.w = s.ey.a[4 * j4 + 3];
-            hpv_st4(slot + (M::C_EY * T + tid) * SP + 4 * j4, o);
-        }
-    }
-}
-
-template <int DIM, int MX, int MY, int HP>
-HPV_HD void hpv_load_state(const float* slot, int T, int tid, HpvState<DIM, MX, MY, HP>& s) {
-    typedef HpvMode<DIM, MX, MY> M;
-    constexpr int SP = HpvSP<HP>::value;
-#pragma unroll
-    for (int j4 = 0; j4 < HP / 4; ++j4) {
-        HpvF4 o = hpv_ld4(slot + (M::C_V * T + tid) * SP + 4 * j4);
-        s.v.a[4 * j4] = o.x; s.v.a[4 * j4 + 1] = o.y; s.v.a[4 * j4 + 2] = o.z; s.v.a[4 * j4 + 3] = o.w;
-        if constexpr (M::DX) {
-            o = hpv_ld4(slot + (M::C_DX * T + tid) * SP + 4 * j4);
-            s.dx.a[4 * j4] = o.x; s.dx.a[4 * j4 + 1] = o.y; s.dx.a[4 * j4 + 2] = o.z; s.dx.a[4 * j4 + 3] = o.w;
-        }
-        if constexpr (M::DY) {
-            o = hpv_ld4(slot + (M::C_DY * T + tid) * SP + 4 * j4);
-            s.dy.a[4 * j4] = o.x; s.dy.a[4 * j4 + 1] = o.y; s.dy.a[4 * j4 + 2] = o.z; s.dy.a[4 * j4 + 3] = o.w;
-        }
-        if constexpr (M::EX) {
-            o = hpv_ld4(slot + (M::C_EX * T + tid) * SP + 4 * j4);
-            s.ex.a[4 * j4] = o.x; s.ex.a[4 * j4 + 1] = o.y; s.ex.a[4 * j4 + 2] = o.z; s.ex.a[4 * j4 + 3] = o.w;
-        }
-        if constexpr (M::EY) {
-            o = hpv_ld4(slot + (M::C_EY * T + tid) * SP + 4 * j4);
-            s.ey.a[4 * j4] = o.x; s.ey.a[4 * j4 + 1] = o.y; s.ey.a[4 * j4 + 2] = o.z; s.ey.a[4 * j4 + 3] = o.w;
-        }
-    }
-}
-
 // Weight-gradient GEMM over the T points of a tile:  D[i][j] += sum_ch sum_p IN[ch][p][i] * ADJ[ch][p][j].
-// 4x4 output tiles, K (points) split over KS threads per tile, partials combined through shared memory in a
-// fixed order (deterministic).  `bias` adds a virtual row of ones in the value channel (-> bias gradient).
-// dst_kind: 0 hidden layer (dst = W[HP][HP], dstb = b), 1 output layer (dst = Wo[HP], dstb = bo),
-//           2 first layer (IN rows = x, y, 1: dst = W1[DIM][HP], dstb = b1).
-HPV_HD void hpv_wgrad_gemm(const HpvCta& c, const float* IN, int spi, const float* ADJ, int spa, int nch,
-                           int NI, int NJ, bool bias, int dst_kind, float* dst, float* dstb, int hp, int dim,
-                           float* scratch) {
+// Register tile of 8 rows (i) x 4 columns (j) per thread, accumulated with packed FFMA2 over column pairs;
+// K (points) split over KS threads per tile, partials combined through shared memory in a fixed order
+// (deterministic).  Per point and channel a thread issues three 128-bit shared loads for 16 FFMA2.
+// NROWS = rows of IN (multiple of 4).  BIAS appends a virtual row of ones in the value channel (-> bias
+// gradient).  KIND: 0 hidden layer (dst = W[HP][HP], dstb = b), 1 output layer (dst = Wo[HP], dstb = bo; only
+// column 0 of ADJ is meaningful), 2 first layer (IN rows = x, y, 1, 0: dst = W1[DIM][HP], dstb = b1).
+template <int SPI, int SPA, int NCH, int NROWS, int NJ, bool BIAS, int KIND, int HP, int DIM>
+HPV_HD void hpv_wgrad_gemm(const HpvCta& c, const float* IN, const float* ADJ, float* dst, float* dstb, float* scratch) {
+    constexpr int RTOT = NROWS + (BIAS ? 1 : 0);
+    constexpr int NI = (RTOT + 7) / 8;
+    constexpr int NTILES = NI * NJ;
     const int T = c.nthreads, tid = c.tid;
-    const int ntiles = (NI + (bias ? 1 : 0)) * NJ;
     int KS = 1;
-    while (KS * 2 * ntiles <= T) KS *= 2;
+    while (KS * 2 * NTILES <= T) KS *= 2;
     const int tau = tid / KS, ks = tid - tau * KS;
-    const bool active = tau < ntiles;
+    const bool active = tau < NTILES;
     const int it = active ? tau / NJ : 0, jt = active ? tau - it * NJ : 0;
-    const bool brow = bias && it == NI;
-    float acc[4][4];
+    // the two 4-row groups of this thread's tile: 0 = rows of IN, 1 = the bias row (ones) first, 2 = empty
+    const int r0 = 8 * it, r1 = 8 * it + 4;
+    const int ty0 = r0 < NROWS ? 0 : ((BIAS && r0 == NROWS) ? 1 : 2);
+    const int ty1 = r1 < NROWS ? 0 : ((BIAS && r1 == NROWS) ? 1 : 2);
+    hpv_pair acc[8][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    for (int i = 0; i < 8; ++i) { acc[i][0] = hpv_pack(0.0f, 0.0f); acc[i][1] = hpv_pack(0.0f, 0.0f); }
     if (active) {
-        for (int ch = 0; ch < nch; ++ch) {
-            if (brow && ch != 0) break;
-            const float* inb = IN + (size_t)ch * T * spi + 4 * it;
-            const float* adb = ADJ + (size_t)ch * T * spa + 4 * jt;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            const float* inb = IN + (size_t)ch * T * SPI;
+            const float* adb = ADJ + (size_t)ch * T * SPA + 4 * jt;
+            const float one = (ch == 0) ? 1.0f : 0.0f;
+#pragma unroll 2
             for (int p = ks; p < T; p += KS) {
-                HpvF4 a4;
-                if (brow) { a4.x = 1.0f; a4.y = a4.z = a4.w = 0.0f; }
-                else a4 = hpv_ld4(inb + p * spi);
-                const HpvF4 b4 = hpv_ld4(adb + p * spa);
-                const float as[4] = {a4.x, a4.y, a4.z, a4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w};
+                HpvF4 a0, a1;
+                a0.x = one; a0.y = a0.z = a0.w = 0.0f;
+                a1 = a0;
+                if (ty0 == 0) a0 = hpv_ld4(inb + p * SPI + r0);
+                else if (ty0 == 2) a0.x = 0.0f;
+                if (ty1 == 0) a1 = hpv_ld4(inb + p * SPI + r1);
+                else if (ty1 == 2) a1.x = 0.0f;
+                const HpvF4 b4 = hpv_ld4(adb + p * SPA);
+                const hpv_pair b01 = hpv_pack(b4.x, b4.y), b23 = hpv_pack(b4.z, b4.w);
+                const float as[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(as[i], bs[j], acc[i][j]);
+                for (int i = 0; i < 8; ++i) {
+                    const hpv_pair ad = hpv_dup(as[i]);
+                    hpv_fma2(acc[i][0], ad, b01);
+                    hpv_fma2(acc[i][1], ad, b23);
+                }
             }
         }
     }
+    float out[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { hpv_unpack(acc[i][0], out[i][0], out[i][1]); hpv_unpack(acc[i][1], out[i][2], out[i][3]); }
     if (KS > 1) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            HpvF4 o; o.x = acc[i][0]; o.y = acc[i][1]; o.z = acc[i][2]; o.w = acc[i][3];
-            hpv_st4(scratch + tid * 16 + 4 * i, o);
+        for (int i = 0; i < 8; ++i) {
+            HpvF4 o; o.x = out[i][0]; o.y = out[i][1]; o.z = out[i][2]; o.w = out[i][3];
+            hpv_st4(scratch + tid * 32 + 4 * i, o);
         }
         hpv_sync(c);
         if (active && ks == 0) {
             for (int s = 1; s < KS; ++s) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const HpvF4 v = hpv_ld4(scratch + (tid + s) * 16 + 4 * i);
-                    acc[i][0] += v.x; acc[i][1] += v.y; acc[i][2] += v.z; acc[i][3] += v.w;
+                for (int i = 0; i < 8; ++i) {
+                    const HpvF4 v = hpv_ld4(scratch + (tid + s) * 32 + 4 * i);
+                    out[i][0] += v.x; out[i][1] += v.y; out[i][2] += v.z; out[i][3] += v.w;
                 }
             }
         }
     }
     if (active && ks == 0) {
-        if (dst_kind == 0) {
-            if (brow) { for (int j = 0; j < 4; ++j) dstb[4 * jt + j] += acc[0][j]; }
-            else for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) dst[(4 * it + i) * hp + 4 * jt + j] += acc[i][j];
-        } else if (dst_kind == 1) {
-            if (brow) dstb[0] += acc[0][0];
-            else for (int i = 0; i < 4; ++i) dst[4 * it + i] += acc[i][0];
-        } else {
-            for (int j = 0; j < 4; ++j) {
-                dst[4 * jt + j] += acc[0][j];
-                if (dim == 2) dst[hp + 4 * jt + j] += acc[1][j];
-                dstb[4 * jt + j] += acc[2][j];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = 8 * it + i;
+            if (KIND == 0) {
+                if (r < NROWS) { for (int j = 0; j < 4; ++j) dst[r * HP + 4 * jt + j] += out[i][j]; }
+                else if (BIAS && r == NROWS) { for (int j = 0; j < 4; ++j) dstb[4 * jt + j] += out[i][j]; }
+            } else if (KIND == 1) {
+                if (r < NROWS) dst[r] += out[i][0];
+                else if (BIAS && r == NROWS) dstb[0] += out[i][0];
+            } else {
+                if (r < DIM) { for (int j = 0; j < 4; ++j) dst[r * HP + 4 * jt + j] += out[i][j]; }
+                else if (r == 2) { for (int j = 0; j < 4; ++j) dstb[4 * jt + j] += out[i][j]; }
             }
         }
     }
@@ -272,15 +265,22 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
     const int T = c.nthreads, tid = c.tid, nhid = a.nhid, top = nhid - 1;
     const HpvBwdSmem<DIM, MX, MY, HP> L(a.theta_pad_n, nhid, T);
     float* sm = reinterpret_cast<float*>(c.smem);
-    float* s_th = sm + L.th;
+    const float* s_th = HPV_THETA(a.theta_pad, a.cslot);
     float* s_gw = sm + L.gw;
     float* s_in0 = sm + L.in0;
     float* s_go = sm + L.go;
     float* s_scr = sm + L.scratch;
     float* s_red = sm + L.red;
-#define HPV_SLOT(l) (sm + L.slots + ((l) == 0 ? 1 : (l) - 1) * L.slot_sz)
+    // Slots (one row of SP floats per thread and channel).  P(l), l = 1..top-1: pre-activations of hidden layer l
+    // kept from the forward recompute, later overwritten by the post-activations (left factor of the W_{l+1}
+    // gradient).  X: the running slot -- post-activations feeding the next layer product, then the adjoint of
+    // the pre-activations of the layer being differentiated, then (in place) the adjoint handed one layer down.
+    // H0: post-activations of the first hidden layer (recomputed), in a slot that is dead by then.
+    float* const X = sm + L.slots + (size_t)(top >= 1 ? top - 1 : 0) * L.slot_sz;
+    float* const H0 = sm + L.slots + (size_t)(top >= 2 ? 0 : 1) * L.slot_sz;
+#define HPV_P(l) (sm + L.slots + (size_t)((l) - 1) * L.slot_sz)
 
-    for (int i = tid; i < a.theta_pad_n; i += T) { s_th[i] = a.theta_pad[i]; s_gw[i] = 0.0f; }
+    for (int i = tid; i < a.theta_pad_n; i += T) s_gw[i] = 0.0f;
     const float eps = a.eps[0];
     float coef[HPV_MAX_TERMS][HPV_NFIELDS], coef1[HPV_MAX_TERMS][HPV_NFIELDS];
     for (int t = 0; t < HPV_MAX_TERMS; ++t)
@@ -296,6 +296,7 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
     const int tile_end = (int)(((long long)(c.bid + 1) * ba.n_tiles) / c.nblocks);
     const float* Wo = s_th + hpv_off_wo(DIM, HP, nhid);
 
+#pragma unroll 1
     for (int tile = tile_begin; tile < tile_end; ++tile) {
         const int gp = tile * T + tid;
         const bool valid = gp < ba.n_points;
@@ -314,20 +315,24 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
             for (int t = 0; t < a.n_terms; ++t) gbar[t] = ba.Gbar[(size_t)t * ba.n_points + gp];
         }
 
-        // ---- forward recompute, keeping the hidden pre-activations of layers 1..top-1 in shared memory ----
-        State pre, h, g;
+        // ---- forward recompute; the pre-activations of hidden layers 1..top-1 stay in their slots ----
+        State pre, g;
         hpv_layer1_pre<DIM, MX, MY, HP>(s_th, x, y, pre);
+#pragma unroll 1
         for (int l = 1; l <= top; ++l) {
-            h = pre;
-            hpv_activate<DIM, MX, MY, HP, ACT>(h);
+            hpv_activate<DIM, MX, MY, HP, ACT>(pre);                     // h_{l-1}
+            hpv_store_state<DIM, MX, MY, HP>(X, T, tid, pre);
             const float* W = s_th + hpv_off_wl(DIM, HP, l);
-            hpv_matmul<DIM, MX, MY, HP>(W, W + HP * HP, h, pre);
-            if (l < top) hpv_store_state<DIM, MX, MY, HP>(HPV_SLOT(l), T, tid, pre);
+            hpv_matmul_slot<DIM, MX, MY, HP>(W, W + HP * HP, X, T, tid, pre);
+            if (l < top) hpv_store_state<DIM, MX, MY, HP>(HPV_P(l), T, tid, pre);
         }
-        h = pre;
-        hpv_activate<DIM, MX, MY, HP, ACT>(h);                  // h_top
+        {
+            State h = pre;                                             // pre = pre-activations of the top layer
+            hpv_activate<DIM, MX, MY, HP, ACT>(h);
+            hpv_store_state<DIM, MX, MY, HP>(X, T, tid, h);
+        }
         float f[HPV_NFIELDS], gf[HPV_NFIELDS];
-        hpv_output<DIM, MX, MY, HP>(Wo, h, f);
+        hpv_output_slot<DIM, MX, MY, HP>(Wo, X, T, tid, f);
 #pragma unroll
         for (int k = 0; k < HPV_NFIELDS; ++k) gf[k] = 0.0f;
         for (int t = 0; t < a.n_terms; ++t) {
@@ -340,8 +345,7 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
             deps = fmaf(gbar[t], d1, deps);
         }
 
-        // ---- output layer: Wo/bo gradient, adjoint of h_top ----
-        hpv_store_state<DIM, MX, MY, HP>(HPV_SLOT(top), T, tid, h);
+        // ---- output layer: Wo/bo gradient (left factor h_top in X), adjoint of h_top ----
         {
             HpvF4 o; o.y = o.z = o.w = 0.0f;
             o.x = gf[0]; hpv_st4(s_go + (M::C_V * T + tid) * 4, o);
@@ -360,33 +364,34 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
             if constexpr (M::EY) g.ey.a[j] = gf[4] * w;
         }
         hpv_sync(c);
-        hpv_wgrad_gemm(c, HPV_SLOT(top), SP, s_go, 4, M::NCH, HP / 4, 1, true, 1,
-                       s_gw + hpv_off_wo(DIM, HP, nhid), s_gw + hpv_off_wo(DIM, HP, nhid) + HP, HP, DIM, s_scr);
+        hpv_wgrad_gemm<SP, 4, M::NCH, HP, 1, true, 1, HP, DIM>(c, X, s_go, s_gw + hpv_off_wo(DIM, HP, nhid),
+                                                                s_gw + hpv_off_wo(DIM, HP, nhid) + HP, s_scr);
         hpv_sync(c);
 
         // ---- hidden layers, top down ----
+#pragma unroll 1
         for (int l = top; l >= 1; --l) {
-            hpv_activate_bwd<DIM, MX, MY, HP, ACT>(pre, g);     // g := adjoint of the pre-activations of layer l
-            hpv_store_state<DIM, MX, MY, HP>(HPV_SLOT(l), T, tid, g);
-            const float* W = s_th + hpv_off_wl(DIM, HP, l);
-            State gn;
-            hpv_matmul_t<DIM, MX, MY, HP>(W, g, gn);             // adjoint of h_{l-1}
-            if (l - 1 >= 1) hpv_load_state<DIM, MX, MY, HP>(HPV_SLOT(l - 1), T, tid, pre);
+            hpv_activate_bwd<DIM, MX, MY, HP, ACT>(pre, g);             // g := adjoint of the pre-activations of layer l
+            hpv_store_state<DIM, MX, MY, HP>(X, T, tid, g);
+            float* INl = (l - 1 >= 1) ? HPV_P(l - 1) : H0;
+            if (l - 1 >= 1) hpv_load_state<DIM, MX, MY, HP>(INl, T, tid, pre);
             else hpv_layer1_pre<DIM, MX, MY, HP>(s_th, x, y, pre);
-            h = pre;
-            hpv_activate<DIM, MX, MY, HP, ACT>(h);              // h_{l-1}: left factor of the W_l gradient
-            hpv_store_state<DIM, MX, MY, HP>(HPV_SLOT(l - 1), T, tid, h);
+            {
+                State h = pre;
+                hpv_activate<DIM, MX, MY, HP, ACT>(h);                  // h_{l-1}: left factor of the W_l gradient
+                hpv_store_state<DIM, MX, MY, HP>(INl, T, tid, h);
+            }
             hpv_sync(c);
             float* gW = s_gw + hpv_off_wl(DIM, HP, l);
-            hpv_wgrad_gemm(c, HPV_SLOT(l - 1), SP, HPV_SLOT(l), SP, M::NCH, HP / 4, HP / 4, true, 0,
-                           gW, gW + HP * HP, HP, DIM, s_scr);
+            hpv_wgrad_gemm<SP, SP, M::NCH, HP, HP / 4, true, 0, HP, DIM>(c, INl, X, gW, gW + HP * HP, s_scr);
             hpv_sync(c);
-            g = gn;
+            hpv_matmul_t_slot<DIM, MX, MY, HP>(s_th + hpv_off_wl(DIM, HP, l), g, X, T, tid);   // adjoint of h_{l-1}, in place
+            hpv_load_state<DIM, MX, MY, HP>(X, T, tid, g);
         }
 
         // ---- first layer ----
         hpv_activate_bwd<DIM, MX, MY, HP, ACT>(pre, g);
-        hpv_store_state<DIM, MX, MY, HP>(HPV_SLOT(0), T, tid, g);
+        hpv_store_state<DIM, MX, MY, HP>(X, T, tid, g);
         {
             HpvF4 o;
             o.x = x; o.y = y; o.z = 1.0f; o.w = 0.0f; hpv_st4(s_in0 + (0 * T + tid) * 4, o);
@@ -400,11 +405,11 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
             float* gW1 = s_gw + hpv_off_w1();
             float* gb1 = s_gw + hpv_off_b1(DIM, HP);
             constexpr int nch1 = 1 + (M::DX ? 1 : 0) + (M::DY ? 1 : 0);
-            hpv_wgrad_gemm(c, s_in0, 4, HPV_SLOT(0), SP, nch1, 1, HP / 4, false, 2, gW1, gb1, HP, DIM, s_scr);
+            hpv_wgrad_gemm<4, SP, nch1, 4, HP / 4, false, 2, HP, DIM>(c, s_in0, X, gW1, gb1, s_scr);
             hpv_sync(c);
         }
     }
-#undef HPV_SLOT
+#undef HPV_P
 
     // ---- publish this CTA's partial gradient ----
     const float dtot = hpv_block_sum(c, s_red, deps);

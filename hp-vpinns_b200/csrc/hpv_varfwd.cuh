@@ -5,9 +5,13 @@
 // sub-graphs).  See DESIGN.md "Forward kernel" for the data flow and the shared-memory plan.
 #pragma once
 #include "hpv_cta.cuh"
+#include "hpv_const.cuh"
+#include "hpv_slot.cuh"
 
+// Shared-memory plan.  The region R is time-shared inside a chunk: first the per-thread activation slot of the
+// MLP phase, then (re-staged from L2) the test-function tables and the first-contraction output P.
 struct HpvFwdSmem {
-    int th, xi1, tab[HPV_NTAB], G, P, red, flag, total;   // offsets in floats
+    int xi1, G, red, flag, R, tab[HPV_NTAB], P, total;   // offsets in floats
     int GS, RMAX;
 };
 
@@ -17,24 +21,26 @@ HPV_HD int hpv_tab_mask(const HpvVarArgs& a) {
     return m;
 }
 
-HPV_HD HpvFwdSmem hpv_fwd_smem(const HpvVarArgs& a) {
+HPV_HD HpvFwdSmem hpv_fwd_smem(const HpvVarArgs& a, int slot_floats) {
     HpvFwdSmem s;
     int o = 0;
-    s.th = o; o += hpv_align4(a.theta_pad_n);
     s.xi1 = o; o += hpv_align4(a.Q);
-    int m = hpv_tab_mask(a);
-    for (int t = 0; t < HPV_NTAB; ++t) {
-        s.tab[t] = -1;
-        if (m & (1 << t)) { s.tab[t] = o; o += a.Q * HPV_NP; }
-    }
     s.GS = hpv_align4(HPV_CT * HPV_THREADS + 2 * a.Q);
     int rmax = (HPV_CT * HPV_THREADS) / a.Q + 2;
     s.RMAX = rmax < a.rows ? rmax : a.rows;
     s.G = o; o += a.n_terms * s.GS;
-    s.P = o; o += a.n_terms * s.RMAX * HPV_NP;
     s.red = o; o += 2 * HPV_THREADS;                    // doubles for the final reduction
     s.flag = o; o += 4;
-    s.total = o;
+    s.R = o;
+    int p = o;
+    int m = hpv_tab_mask(a);
+    for (int t = 0; t < HPV_NTAB; ++t) {
+        s.tab[t] = -1;
+        if (m & (1 << t)) { s.tab[t] = p; p += a.Q * HPV_NP; }
+    }
+    s.P = p; p += a.n_terms * s.RMAX * HPV_NP;
+    const int proj = p - o;
+    s.total = o + (proj > slot_floats ? proj : slot_floats);
     return s;
 }
 
@@ -45,10 +51,7 @@ HPV_HD float hpv_term_scale(const HpvTerm& t, float hwx, float hwy) {
     return c;
 }
 
-// Cooperative copy of the launch-invariant data into shared memory (parameters, nodes, tables).
-HPV_HD void hpv_stage_common(const HpvCta& c, const HpvVarArgs& a, float* sm, int o_th, int o_xi1, const int* o_tab) {
-    for (int i = c.tid; i < a.theta_pad_n; i += c.nthreads) sm[o_th + i] = a.theta_pad[i];
-    for (int i = c.tid; i < a.Q; i += c.nthreads) sm[o_xi1 + i] = a.xi1[i];
+HPV_HD void hpv_stage_tables(const HpvCta& c, const HpvVarArgs& a, float* sm, const int* o_tab) {
     for (int t = 0; t < HPV_NTAB; ++t) {
         if (o_tab[t] < 0) continue;
         const float* src = a.tab[t];
@@ -59,18 +62,19 @@ HPV_HD void hpv_stage_common(const HpvCta& c, const HpvVarArgs& a, float* sm, in
 
 template <int DIM, int MX, int MY, int HP, int ACT>
 HPV_HD void hpv_varfwd_body(const HpvCta& c, const HpvVarArgs& a) {
-    const HpvFwdSmem L = hpv_fwd_smem(a);
+    const int T = c.nthreads, tid = c.tid;
+    const HpvFwdSmem L = hpv_fwd_smem(a, HpvMode<DIM, MX, MY>::NCH * T * HpvSP<HP>::value);
     float* sm = reinterpret_cast<float*>(c.smem);
-    float* s_th = sm + L.th;
+    const float* th = HPV_THETA(a.theta_pad, a.cslot);
     float* s_xi1 = sm + L.xi1;
     float* s_G = sm + L.G;
     float* s_P = sm + L.P;
+    float* s_slot = sm + L.R;
     float* s_red = sm + L.red;
     int* s_flag = reinterpret_cast<int*>(sm + L.flag);
-    const int T = c.nthreads, tid = c.tid;
     const int Q = a.Q;
 
-    hpv_stage_common(c, a, sm, L.th, L.xi1, L.tab);
+    for (int i = tid; i < Q; i += T) s_xi1[i] = a.xi1[i];
     const float eps = a.eps[0];
     float coef[HPV_MAX_TERMS][HPV_NFIELDS];
     for (int t = 0; t < HPV_MAX_TERMS; ++t)
@@ -108,6 +112,7 @@ HPV_HD void hpv_varfwd_body(const HpvCta& c, const HpvVarArgs& a) {
         hpv_sync(c);
 
         // (2) network and input derivatives at the quadrature points -> projected fields
+#pragma unroll 1
         for (int it = 0; it < nt; ++it) {
             const int p = p0 + it * T + tid;
             if (p < p1) {
@@ -115,7 +120,7 @@ HPV_HD void hpv_varfwd_body(const HpvCta& c, const HpvVarArgs& a) {
                 const float x = fmaf(hwx, s_xi1[i], lox);
                 const float y = (DIM == 2) ? fmaf(hwy, s_xi1[j], loy) : 0.0f;
                 float f[HPV_NFIELDS];
-                hpv_net_point<DIM, MX, MY, HP, ACT>(s_th, a.nhid, x, y, f);
+                hpv_net_point_slot<DIM, MX, MY, HP, ACT>(th, a.nhid, x, y, s_slot, T, tid, f);
                 for (int t = 0; t < a.n_terms; ++t) {
                     float g = 0.0f;
 #pragma unroll
@@ -124,6 +129,10 @@ HPV_HD void hpv_varfwd_body(const HpvCta& c, const HpvVarArgs& a) {
                 }
             }
         }
+        hpv_sync(c);
+
+        // the activation slot is dead now: bring the test-function tables into the same region
+        hpv_stage_tables(c, a, sm, L.tab);
         hpv_sync(c);
 
         // (3) first contraction, over the x index:  P_t[jl][r] = c_t * sum_i G_t[jl][i] * R_t[i][r]

@@ -76,7 +76,7 @@ int emu_bwd(const Key& k, const HpvBwdArgs& a, int grid, int block) {
 }
 
 int emu_pts(const Key& k, const HpvPointArgs& a, float* gbar, int grid) {
-    const size_t smem = (size_t)(hpv_align4(a.theta_pad_n) + HPV_THREADS) * 4;
+    const size_t smem = (size_t)(HPV_THREADS + hpv_slot_floats(k.dim, k.mx, k.my, k.hp, HPV_THREADS)) * 4;
 #define CALL(DIM, MX, MY, HP, ACT) run_grid(grid, HPV_THREADS, smem, [&](const HpvCta& c) { hpv_points_body<DIM, MX, MY, HP, ACT>(c, a, gbar); })
     EMU_DISPATCH(CALL)
 #undef CALL
@@ -109,6 +109,8 @@ int hpv_emu_varloss(int dim, const int* layers, int n_layers, int act, int Q, co
     if (dim == 1) nty = 1;
     std::vector<float> tabs[HPV_NTAB];
     hpv_build_tables(Q, N, w, T, D1, D2, d1b, fm.fold_boundary, tabs);
+    std::vector<float> nat[HPV_NTAB];
+    hpv_natural_tables(Q, tabs, nat);
     std::vector<float> xi1(Q);
     for (int q = 0; q < Q; ++q) xi1[q] = (float)(xi[q] + 1.0);
     std::vector<float> th;
@@ -137,7 +139,8 @@ int hpv_emu_varloss(int dim, const int* layers, int n_layers, int act, int Q, co
     memset(&a, 0, sizeof(a));
     a.theta_pad = th.data(); a.theta_pad_n = net.theta_pad_n; a.nhid = net.nhid; a.eps = &epsf;
     a.Q = Q; a.rows = rows; a.xi1 = xi1.data();
-    for (int t = 0; t < HPV_NTAB; ++t) a.tab[t] = tabs[t].data();
+    for (int t = 0; t < HPV_NTAB; ++t) { a.tab[t] = tabs[t].data(); a.tabN[t] = nat[t].data(); }
+    a.QP = hpv_align4(Q);
     a.n_el = n_el; a.el_geom = geom.data(); a.el_ntest = nt.data(); a.ntx = ntx; a.nty = nty;
     a.F = fm.has_rhs && F_ext ? F.data() : nullptr;
     a.n_terms = fm.n_terms;
@@ -149,7 +152,8 @@ int hpv_emu_varloss(int dim, const int* layers, int n_layers, int act, int Q, co
     a.Res = Res.data(); a.el_loss = el_loss.data(); a.loss = &loss; a.loss_scale = 1.0f;
 
     Key k{dim, fm.mx, fm.my, net.hp, act};
-    const HpvFwdSmem fs = hpv_fwd_smem(a);
+    int cmx = fm.mx, cmy = fm.my; hpv_canon_mode(dim, cmx, cmy);
+    const HpvFwdSmem fs = hpv_fwd_smem(a, hpv_slot_floats(dim, cmx, cmy, net.hp, HPV_THREADS));
     int r = emu_fwd(k, a, part.n_ctas, (size_t)fs.total * 4);
     if (r) return r;
     if (counters[n_el] != 0u) return -7;                 // self-resetting counters must be back at zero

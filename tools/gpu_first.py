@@ -51,4 +51,4 @@ for what, nm in ((0, "forward"), (1, "adjproj"), (2, "mlpbwd"), (3, "reduce+unpa
 e3.configure_training(wv=1.0)
 h = e3.train_steps(20)
 e3.sync(); t0 = time.time(); h = e3.train_steps(200); t1 = time.time()
-print("C3 train step %.1f us/step (wall, 200 steps) loss %.4e -> %.4e" % ((t1 - t0) / 200 * 1e6, h[0], h[-1]), flush=True)
+print("C3 train step %.1f us/step (wall, 200 steps) loss %.4e -> %.4e" % ((t1 - t0) / 200 * 1e6, h[0, 0], h[-1, 0]), flush=True)
