@@ -74,7 +74,8 @@ def build_workload(name, rank=0, world=1):
     D1, D2 = GJ.dTest_fcn(N, X)
     g = np.linspace(-1, 1, ne + 1)
     n_el = ne * ne
-    e0, e1 = (n_el * rank) // world, (n_el * (rank + 1)) // world      # contiguous block of the (ex, ey) order
+    from hpv_b200.distributed import shard_bounds
+    e0, e1 = shard_bounds(n_el, rank, world)                            # contiguous block of the (ex, ey) order
     lo = np.array([[g[e // ne], g[e % ne]] for e in range(e0, e1)])
     hi = np.array([[g[e // ne + 1], g[e % ne + 1]] for e in range(e0, e1)])
     A = T * W[None, :]
@@ -281,11 +282,8 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     eng.set_stream(stream.cuda_stream)
-    ptr, nred = eng.reduce_buffer()
-
-    class _Cai:
-        __cuda_array_interface__ = {"shape": (nred,), "typestr": "<f4", "data": (ptr, False), "version": 3}
-    red = torch.as_tensor(_Cai(), device="cuda") if world > 1 else None
+    from hpv_b200.distributed import reduce_tensor
+    red = reduce_tensor(eng) if world > 1 else None
 
     def step():
         eng.loss_and_grad()

@@ -106,6 +106,28 @@ __global__ void __launch_bounds__(256) hpv_ffma_probe_kernel(float* out, int ite
                 for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], hpv_probe_c[i], b0);
             }
         }
+    } else if (variant == 3) {
+        // the form the MLP kernels issue: FFMA2 acc, x.F32 (broadcast), UR pair from constant memory, acc
+        unsigned long long p[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm("mov.b64 %0, {%1, %2};" : "=l"(p[i]) : "f"(acc[2 * i]), "f"(acc[2 * i + 1]));
+        unsigned long long xa, xb;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(xa) : "f"(a0));
+        asm("mov.b64 %0, {%1, %1};" : "=l"(xb) : "f"(b0));
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    unsigned long long w;
+                    const int wi = 2 * ((i + it) & 7);           // uniform, loop-dependent: forces a fresh LDCU
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(w) : "f"(hpv_probe_c[wi]), "f"(hpv_probe_c[wi + 1]));
+                    asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p[i]) : "l"((r & 1) ? xa : xb), "l"(w));
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * i]), "=f"(acc[2 * i + 1]) : "l"(p[i]));
     } else {
         unsigned long long pa, pb, p[8];
         asm("mov.b64 %0, {%1, %2};" : "=l"(pa) : "f"(a0), "f"(a0 * 0.99999f));
