@@ -3,6 +3,7 @@
 // compute entry point fails with HPV_ERR_CUDA.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdint.h>
 #include <string>
@@ -159,8 +160,13 @@ int plan_bwd(hpv_ctx* c, int mx, int my, int& block, int& ctas_per_sm, size_t& s
     va.theta_pad_n = c->net.theta_pad_n; va.nhid = c->net.nhid;
     HpvBwdArgs ba; memset(&ba, 0, sizeof(ba)); ba.v = va;
     int best_threads = 0;
-    const int cand[3] = {128, 256, 64};
-    for (int ci = 0; ci < 3; ++ci) {
+    int cand[3] = {128, 256, 64};
+    int ncand = 3;
+    if (const char* ev = getenv("HPV_BWD_BLOCK")) {          // tuning override: 64, 128 or 256
+        const int v = atoi(ev);
+        if (v == 64 || v == 128 || v == 256) { cand[0] = v; ncand = 1; }
+    }
+    for (int ci = 0; ci < ncand; ++ci) {
         HpvLaunch l; memset(&l, 0, sizeof(l));
         long long out = 0;
         l.kind = HPV_K_MLPBWD; l.op = 2; l.block = cand[ci]; l.bwd = &ba; l.out = &out;

@@ -73,8 +73,9 @@ struct HpvMode {
     static constexpr int C_EY = C_EX + (EX ? 1 : 0);
 };
 
+// A channel of one layer at one point: HP units held as HP/2 packed pairs (units 2m, 2m+1).
 template <int HP, bool ON>
-struct HpvVec { float a[ON ? HP : 1]; };
+struct HpvVec { hpv_pair p[ON ? HP / 2 : 1]; };
 
 // Activations of one layer at one point: value and the carried tangents.
 template <int DIM, int MX, int MY, int HP>
@@ -93,17 +94,20 @@ HPV_HD void hpv_layer1_pre(const float* th, float x, float y, HpvState<DIM, MX, 
     typedef HpvMode<DIM, MX, MY> M;
     const float* W1 = th + hpv_off_w1();
     const float* b1 = th + hpv_off_b1(DIM, HP);
+    const hpv_pair xx = hpv_dup(x), yy = hpv_dup(y);
 #pragma unroll
-    for (int j = 0; j < HP; ++j) {
-        const float wx = W1[j];
-        const float wy = (DIM == 2) ? W1[HP + j] : 0.0f;
-        float zz = fmaf(x, wx, b1[j]);
-        if constexpr (DIM == 2) zz = fmaf(y, wy, zz);
-        z.v.a[j] = zz;
-        if constexpr (M::DX) z.dx.a[j] = wx;
-        if constexpr (M::DY) z.dy.a[j] = wy;
-        if constexpr (M::EX) z.ex.a[j] = 0.0f;
-        if constexpr (M::EY) z.ey.a[j] = 0.0f;
+    for (int m = 0; m < HP / 2; ++m) {
+        const hpv_pair wx = hpv_pack(W1[2 * m], W1[2 * m + 1]);
+        hpv_pair zz = hpv_fma2r(xx, wx, hpv_pack(b1[2 * m], b1[2 * m + 1]));
+        if constexpr (DIM == 2) {
+            const hpv_pair wy = hpv_pack(W1[HP + 2 * m], W1[HP + 2 * m + 1]);
+            zz = hpv_fma2r(yy, wy, zz);
+            if constexpr (M::DY) z.dy.p[m] = wy;
+        }
+        z.v.p[m] = zz;
+        if constexpr (M::DX) z.dx.p[m] = wx;
+        if constexpr (M::EX) z.ex.p[m] = hpv_dup(0.0f);
+        if constexpr (M::EY) z.ey.p[m] = hpv_dup(0.0f);
     }
 }
 
@@ -119,47 +123,42 @@ HPV_HD void hpv_tanh2(hpv_pair z, hpv_pair& a, hpv_pair& s1) {
     s1 = hpv_fma2r(hpv_mul2(a, a), hpv_dup(-1.0f), hpv_dup(1.0f));
 }
 
-// Pre-activations (z, dz, d2z) -> post-activations (h, dh, d2h), in place.
+// Activation value and its first three derivatives for a pair of units.
+template <int ACT>
+HPV_HD void hpv_act2(hpv_pair z, hpv_pair& a, hpv_pair& s1, hpv_pair& s2, hpv_pair& s3, bool need3) {
+    if constexpr (ACT == HPV_ACT_TANH) {
+        hpv_tanh2(z, a, s1);
+        s2 = hpv_mul2(hpv_mul2(a, s1), hpv_dup(-2.0f));
+        if (need3) s3 = hpv_mul2(hpv_mul2(s1, hpv_fma2r(hpv_mul2(a, a), hpv_dup(-3.0f), hpv_dup(1.0f))), hpv_dup(-2.0f));
+    } else {
+        float z0, z1, a0, a1, b0, b1, c0, c1;
+        hpv_unpack(z, z0, z1);
+        hpv_act<ACT>(z0, a0, b0, c0);
+        hpv_act<ACT>(z1, a1, b1, c1);
+        a = hpv_pack(a0, a1); s1 = hpv_pack(b0, b1); s2 = hpv_pack(c0, c1);
+        if (need3) s3 = hpv_pack(hpv_act_s3<ACT>(a0, b0), hpv_act_s3<ACT>(a1, b1));
+    }
+}
+
+// Pre-activations (z, dz, d2z) -> post-activations (h, dh, d2h), in place, on packed pairs of units.
 //   h = s(z);  dh = s'(z) dz;  d2h = s''(z) dz^2 + s'(z) d2z
-// tanh runs on packed pairs of units (FMUL2/FFMA2: half the issue slots of the scalar form).
 template <int DIM, int MX, int MY, int HP, int ACT>
 HPV_HD void hpv_activate(HpvState<DIM, MX, MY, HP>& s) {
     typedef HpvMode<DIM, MX, MY> M;
-    if constexpr (ACT == HPV_ACT_TANH) {
 #pragma unroll
-        for (int j = 0; j < HP; j += 2) {
-            hpv_pair a, s1;
-            hpv_tanh2(hpv_pack(s.v.a[j], s.v.a[j + 1]), a, s1);
-            hpv_unpack(a, s.v.a[j], s.v.a[j + 1]);
-            hpv_pair s2;
-            if constexpr (M::EX || M::EY) s2 = hpv_mul2(hpv_mul2(a, s1), hpv_dup(-2.0f));
-            if constexpr (M::DX) {
-                const hpv_pair dz = hpv_pack(s.dx.a[j], s.dx.a[j + 1]);
-                if constexpr (M::EX) {
-                    const hpv_pair e = hpv_fma2r(hpv_mul2(s2, dz), dz, hpv_mul2(s1, hpv_pack(s.ex.a[j], s.ex.a[j + 1])));
-                    hpv_unpack(e, s.ex.a[j], s.ex.a[j + 1]);
-                }
-                hpv_unpack(hpv_mul2(s1, dz), s.dx.a[j], s.dx.a[j + 1]);
-            }
-            if constexpr (M::DY) {
-                const hpv_pair dz = hpv_pack(s.dy.a[j], s.dy.a[j + 1]);
-                if constexpr (M::EY) {
-                    const hpv_pair e = hpv_fma2r(hpv_mul2(s2, dz), dz, hpv_mul2(s1, hpv_pack(s.ey.a[j], s.ey.a[j + 1])));
-                    hpv_unpack(e, s.ey.a[j], s.ey.a[j + 1]);
-                }
-                hpv_unpack(hpv_mul2(s1, dz), s.dy.a[j], s.dy.a[j + 1]);
-            }
+    for (int m = 0; m < HP / 2; ++m) {
+        hpv_pair a, s1, s2, s3;
+        hpv_act2<ACT>(s.v.p[m], a, s1, s2, s3, false);
+        s.v.p[m] = a;
+        if constexpr (M::DX) {
+            const hpv_pair dz = s.dx.p[m];
+            if constexpr (M::EX) s.ex.p[m] = hpv_fma2r(hpv_mul2(s2, dz), dz, hpv_mul2(s1, s.ex.p[m]));
+            s.dx.p[m] = hpv_mul2(s1, dz);
         }
-    } else {
-#pragma unroll
-        for (int j = 0; j < HP; ++j) {
-            float a, s1, s2;
-            hpv_act<ACT>(s.v.a[j], a, s1, s2);
-            s.v.a[j] = a;
-            if constexpr (M::EX) s.ex.a[j] = fmaf(s2 * s.dx.a[j], s.dx.a[j], s1 * s.ex.a[j]);
-            if constexpr (M::EY) s.ey.a[j] = fmaf(s2 * s.dy.a[j], s.dy.a[j], s1 * s.ey.a[j]);
-            if constexpr (M::DX) s.dx.a[j] = s1 * s.dx.a[j];
-            if constexpr (M::DY) s.dy.a[j] = s1 * s.dy.a[j];
+        if constexpr (M::DY) {
+            const hpv_pair dz = s.dy.p[m];
+            if constexpr (M::EY) s.ey.p[m] = hpv_fma2r(hpv_mul2(s2, dz), dz, hpv_mul2(s1, s.ey.p[m]));
+            s.dy.p[m] = hpv_mul2(s1, dz);
         }
     }
 }
@@ -173,73 +172,35 @@ HPV_HD void hpv_activate(HpvState<DIM, MX, MY, HP>& s) {
 template <int DIM, int MX, int MY, int HP, int ACT>
 HPV_HD void hpv_activate_bwd(const HpvState<DIM, MX, MY, HP>& z, HpvState<DIM, MX, MY, HP>& g) {
     typedef HpvMode<DIM, MX, MY> M;
-    if constexpr (ACT == HPV_ACT_TANH) {
 #pragma unroll
-        for (int j = 0; j < HP; j += 2) {
-            hpv_pair a, s1;
-            hpv_tanh2(hpv_pack(z.v.a[j], z.v.a[j + 1]), a, s1);
-            hpv_pair zb = hpv_mul2(hpv_pack(g.v.a[j], g.v.a[j + 1]), s1);
-            hpv_pair s2, s3;
-            if constexpr (M::DX || M::DY) s2 = hpv_mul2(hpv_mul2(a, s1), hpv_dup(-2.0f));
-            if constexpr (M::EX || M::EY)
-                s3 = hpv_mul2(hpv_mul2(s1, hpv_fma2r(hpv_mul2(a, a), hpv_dup(-3.0f), hpv_dup(1.0f))), hpv_dup(-2.0f));
-            if constexpr (M::DX) {
-                const hpv_pair dz = hpv_pack(z.dx.a[j], z.dx.a[j + 1]), gd = hpv_pack(g.dx.a[j], g.dx.a[j + 1]);
-                zb = hpv_fma2r(hpv_mul2(gd, s2), dz, zb);
-                hpv_pair dzb = hpv_mul2(gd, s1);
-                if constexpr (M::EX) {
-                    const hpv_pair d2z = hpv_pack(z.ex.a[j], z.ex.a[j + 1]), ge = hpv_pack(g.ex.a[j], g.ex.a[j + 1]);
-                    zb = hpv_fma2r(ge, hpv_fma2r(hpv_mul2(s3, dz), dz, hpv_mul2(s2, d2z)), zb);
-                    dzb = hpv_fma2r(hpv_mul2(hpv_mul2(ge, s2), hpv_dup(2.0f)), dz, dzb);
-                    hpv_unpack(hpv_mul2(ge, s1), g.ex.a[j], g.ex.a[j + 1]);
-                }
-                hpv_unpack(dzb, g.dx.a[j], g.dx.a[j + 1]);
+    for (int m = 0; m < HP / 2; ++m) {
+        hpv_pair a, s1, s2, s3;
+        hpv_act2<ACT>(z.v.p[m], a, s1, s2, s3, M::EX || M::EY);
+        hpv_pair zb = hpv_mul2(g.v.p[m], s1);
+        if constexpr (M::DX) {
+            const hpv_pair dz = z.dx.p[m], gd = g.dx.p[m];
+            zb = hpv_fma2r(hpv_mul2(gd, s2), dz, zb);
+            hpv_pair dzb = hpv_mul2(gd, s1);
+            if constexpr (M::EX) {
+                const hpv_pair d2z = z.ex.p[m], ge = g.ex.p[m];
+                zb = hpv_fma2r(ge, hpv_fma2r(hpv_mul2(s3, dz), dz, hpv_mul2(s2, d2z)), zb);
+                dzb = hpv_fma2r(hpv_mul2(hpv_mul2(ge, s2), hpv_dup(2.0f)), dz, dzb);
+                g.ex.p[m] = hpv_mul2(ge, s1);
             }
-            if constexpr (M::DY) {
-                const hpv_pair dz = hpv_pack(z.dy.a[j], z.dy.a[j + 1]), gd = hpv_pack(g.dy.a[j], g.dy.a[j + 1]);
-                zb = hpv_fma2r(hpv_mul2(gd, s2), dz, zb);
-                hpv_pair dzb = hpv_mul2(gd, s1);
-                if constexpr (M::EY) {
-                    const hpv_pair d2z = hpv_pack(z.ey.a[j], z.ey.a[j + 1]), ge = hpv_pack(g.ey.a[j], g.ey.a[j + 1]);
-                    zb = hpv_fma2r(ge, hpv_fma2r(hpv_mul2(s3, dz), dz, hpv_mul2(s2, d2z)), zb);
-                    dzb = hpv_fma2r(hpv_mul2(hpv_mul2(ge, s2), hpv_dup(2.0f)), dz, dzb);
-                    hpv_unpack(hpv_mul2(ge, s1), g.ey.a[j], g.ey.a[j + 1]);
-                }
-                hpv_unpack(dzb, g.dy.a[j], g.dy.a[j + 1]);
-            }
-            hpv_unpack(zb, g.v.a[j], g.v.a[j + 1]);
+            g.dx.p[m] = dzb;
         }
-    } else {
-#pragma unroll
-        for (int j = 0; j < HP; ++j) {
-            float a, s1, s2;
-            hpv_act<ACT>(z.v.a[j], a, s1, s2);
-            float zb = g.v.a[j] * s1;
-            if constexpr (M::DX) {
-                const float dz = z.dx.a[j];
-                zb = fmaf(g.dx.a[j] * s2, dz, zb);
-                float dzb = g.dx.a[j] * s1;
-                if constexpr (M::EX) {
-                    const float s3 = hpv_act_s3<ACT>(a, s1), d2z = z.ex.a[j];
-                    zb = fmaf(g.ex.a[j], fmaf(s3 * dz, dz, s2 * d2z), zb);
-                    dzb = fmaf(2.0f * g.ex.a[j] * s2, dz, dzb);
-                    g.ex.a[j] = g.ex.a[j] * s1;
-                }
-                g.dx.a[j] = dzb;
+        if constexpr (M::DY) {
+            const hpv_pair dz = z.dy.p[m], gd = g.dy.p[m];
+            zb = hpv_fma2r(hpv_mul2(gd, s2), dz, zb);
+            hpv_pair dzb = hpv_mul2(gd, s1);
+            if constexpr (M::EY) {
+                const hpv_pair d2z = z.ey.p[m], ge = g.ey.p[m];
+                zb = hpv_fma2r(ge, hpv_fma2r(hpv_mul2(s3, dz), dz, hpv_mul2(s2, d2z)), zb);
+                dzb = hpv_fma2r(hpv_mul2(hpv_mul2(ge, s2), hpv_dup(2.0f)), dz, dzb);
+                g.ey.p[m] = hpv_mul2(ge, s1);
             }
-            if constexpr (M::DY) {
-                const float dz = z.dy.a[j];
-                zb = fmaf(g.dy.a[j] * s2, dz, zb);
-                float dzb = g.dy.a[j] * s1;
-                if constexpr (M::EY) {
-                    const float s3 = hpv_act_s3<ACT>(a, s1), d2z = z.ey.a[j];
-                    zb = fmaf(g.ey.a[j], fmaf(s3 * dz, dz, s2 * d2z), zb);
-                    dzb = fmaf(2.0f * g.ey.a[j] * s2, dz, dzb);
-                    g.ey.a[j] = g.ey.a[j] * s1;
-                }
-                g.dy.a[j] = dzb;
-            }
-            g.v.a[j] = zb;
+            g.dy.p[m] = dzb;
         }
+        g.v.p[m] = zb;
     }
 }

@@ -19,27 +19,42 @@ HPV_HD int hpv_mode_nch(int dim, int mx, int my) {
 }
 HPV_HD int hpv_slot_floats(int dim, int mx, int my, int hp, int T) { return hpv_mode_nch(dim, mx, my) * T * hpv_sp(hp); }
 
-// Visit the channels a mode carries: f(array of HP floats, channel slot index).
+// Visit the channels a mode carries: f(array of HP/2 packed pairs, channel slot index).
 template <class M, class S, class F>
 HPV_HD void hpv_each_ch(S& s, F f) {
-    f(s.v.a, M::C_V);
-    if constexpr (M::DX) f(s.dx.a, M::C_DX);
-    if constexpr (M::DY) f(s.dy.a, M::C_DY);
-    if constexpr (M::EX) f(s.ex.a, M::C_EX);
-    if constexpr (M::EY) f(s.ey.a, M::C_EY);
+    f(s.v.p, M::C_V);
+    if constexpr (M::DX) f(s.dx.p, M::C_DX);
+    if constexpr (M::DY) f(s.dy.p, M::C_DY);
+    if constexpr (M::EX) f(s.ex.p, M::C_EX);
+    if constexpr (M::EY) f(s.ey.p, M::C_EY);
+}
+
+// 128-bit shared-memory access of two packed pairs (4 consecutive units of a slot row).
+HPV_HD void hpv_st_pairs(float* p, hpv_pair a, hpv_pair b) {
+#if defined(__CUDA_ARCH__)
+    ulonglong2 v; v.x = a; v.y = b;
+    *reinterpret_cast<ulonglong2*>(p) = v;
+#else
+    p[0] = a.lo; p[1] = a.hi; p[2] = b.lo; p[3] = b.hi;
+#endif
+}
+HPV_HD void hpv_ld_pairs(const float* p, hpv_pair& a, hpv_pair& b) {
+#if defined(__CUDA_ARCH__)
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
+    a = v.x; b = v.y;
+#else
+    a.lo = p[0]; a.hi = p[1]; b.lo = p[2]; b.hi = p[3];
+#endif
 }
 
 template <int DIM, int MX, int MY, int HP>
 HPV_HD void hpv_store_state(float* slot, int T, int tid, const HpvState<DIM, MX, MY, HP>& s) {
     typedef HpvMode<DIM, MX, MY> M;
     constexpr int SP = HpvSP<HP>::value;
-    hpv_each_ch<M>(s, [&](const float* a, int c) {
+    hpv_each_ch<M>(s, [&](const hpv_pair* a, int c) {
         float* row = slot + ((size_t)c * T + tid) * SP;
 #pragma unroll
-        for (int j4 = 0; j4 < HP / 4; ++j4) {
-            HpvF4 o; o.x = a[4 * j4]; o.y = a[4 * j4 + 1]; o.z = a[4 * j4 + 2]; o.w = a[4 * j4 + 3];
-            hpv_st4(row + 4 * j4, o);
-        }
+        for (int j4 = 0; j4 < HP / 4; ++j4) hpv_st_pairs(row + 4 * j4, a[2 * j4], a[2 * j4 + 1]);
     });
 }
 
@@ -47,13 +62,10 @@ template <int DIM, int MX, int MY, int HP>
 HPV_HD void hpv_load_state(const float* slot, int T, int tid, HpvState<DIM, MX, MY, HP>& s) {
     typedef HpvMode<DIM, MX, MY> M;
     constexpr int SP = HpvSP<HP>::value;
-    hpv_each_ch<M>(s, [&](float* a, int c) {
+    hpv_each_ch<M>(s, [&](hpv_pair* a, int c) {
         const float* row = slot + ((size_t)c * T + tid) * SP;
 #pragma unroll
-        for (int j4 = 0; j4 < HP / 4; ++j4) {
-            const HpvF4 o = hpv_ld4(row + 4 * j4);
-            a[4 * j4] = o.x; a[4 * j4 + 1] = o.y; a[4 * j4 + 2] = o.z; a[4 * j4 + 3] = o.w;
-        }
+        for (int j4 = 0; j4 < HP / 4; ++j4) hpv_ld_pairs(row + 4 * j4, a[2 * j4], a[2 * j4 + 1]);
     });
 }
 
@@ -65,11 +77,10 @@ HPV_HD void hpv_matmul_slot(const float* W, const float* b, const float* slot, i
     constexpr int SP = HpvSP<HP>::value, NCH = M::NCH;
     hpv_pair acc[NCH][HP / 2];
 #pragma unroll
-    for (int j4 = 0; j4 < HP / 4; ++j4) {
-        acc[0][2 * j4] = hpv_pack(b[4 * j4], b[4 * j4 + 1]);
-        acc[0][2 * j4 + 1] = hpv_pack(b[4 * j4 + 2], b[4 * j4 + 3]);
+    for (int m = 0; m < HP / 2; ++m) {
+        acc[0][m] = hpv_pack(b[2 * m], b[2 * m + 1]);
 #pragma unroll
-        for (int c = 1; c < NCH; ++c) { acc[c][2 * j4] = hpv_pack(0.0f, 0.0f); acc[c][2 * j4 + 1] = hpv_pack(0.0f, 0.0f); }
+        for (int c = 1; c < NCH; ++c) acc[c][m] = hpv_dup(0.0f);
     }
     const float* row = slot + (size_t)tid * SP;
 #pragma unroll 1
@@ -85,21 +96,18 @@ HPV_HD void hpv_matmul_slot(const float* W, const float* b, const float* slot, i
             const float* wr = W + (4 * i4 + k) * HP;
             hpv_pair xd[NCH];
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) xd[c] = hpv_pack(x[c][k], x[c][k]);
+            for (int c = 0; c < NCH; ++c) xd[c] = hpv_dup(x[c][k]);
 #pragma unroll
-            for (int j4 = 0; j4 < HP / 4; ++j4) {
-                const hpv_pair w0 = hpv_pack(wr[4 * j4], wr[4 * j4 + 1]), w1 = hpv_pack(wr[4 * j4 + 2], wr[4 * j4 + 3]);
+            for (int m = 0; m < HP / 2; ++m) {
+                const hpv_pair w = hpv_pack(wr[2 * m], wr[2 * m + 1]);
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    hpv_fma2(acc[c][2 * j4], xd[c], w0);
-                    hpv_fma2(acc[c][2 * j4 + 1], xd[c], w1);
-                }
+                for (int c = 0; c < NCH; ++c) hpv_fma2(acc[c][m], xd[c], w);
             }
         }
     }
-    hpv_each_ch<M>(out, [&](float* a, int c) {
+    hpv_each_ch<M>(out, [&](hpv_pair* a, int c) {
 #pragma unroll
-        for (int j2 = 0; j2 < HP / 2; ++j2) hpv_unpack(acc[c][j2], a[2 * j2], a[2 * j2 + 1]);
+        for (int m = 0; m < HP / 2; ++m) a[m] = acc[c][m];
     });
 }
 
@@ -109,11 +117,8 @@ template <int DIM, int MX, int MY, int HP>
 HPV_HD void hpv_matmul_t_slot(const float* W, const HpvState<DIM, MX, MY, HP>& in, float* slot, int T, int tid) {
     typedef HpvMode<DIM, MX, MY> M;
     constexpr int SP = HpvSP<HP>::value, NCH = M::NCH;
-    hpv_pair inp[NCH][HP / 2];
-    hpv_each_ch<M>(in, [&](const float* a, int c) {
-#pragma unroll
-        for (int j2 = 0; j2 < HP / 2; ++j2) inp[c][j2] = hpv_pack(a[2 * j2], a[2 * j2 + 1]);
-    });
+    const hpv_pair* inp[NCH];
+    hpv_each_ch<M>(in, [&](const hpv_pair* a, int c) { inp[c] = a; });
     float* row = slot + (size_t)tid * SP;
 #pragma unroll 1
     for (int i4 = 0; i4 < HP / 4; ++i4) {
@@ -123,15 +128,12 @@ HPV_HD void hpv_matmul_t_slot(const float* W, const HpvState<DIM, MX, MY, HP>& i
             const float* wr = W + (4 * i4 + k) * HP;
             hpv_pair s[NCH];
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) s[c] = hpv_pack(0.0f, 0.0f);
+            for (int c = 0; c < NCH; ++c) s[c] = hpv_dup(0.0f);
 #pragma unroll
-            for (int j4 = 0; j4 < HP / 4; ++j4) {
-                const hpv_pair w0 = hpv_pack(wr[4 * j4], wr[4 * j4 + 1]), w1 = hpv_pack(wr[4 * j4 + 2], wr[4 * j4 + 3]);
+            for (int m = 0; m < HP / 2; ++m) {
+                const hpv_pair w = hpv_pack(wr[2 * m], wr[2 * m + 1]);
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    hpv_fma2(s[c], inp[c][2 * j4], w0);
-                    hpv_fma2(s[c], inp[c][2 * j4 + 1], w1);
-                }
+                for (int c = 0; c < NCH; ++c) hpv_fma2(s[c], inp[c][m], w);
             }
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {

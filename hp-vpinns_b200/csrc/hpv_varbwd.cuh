@@ -355,13 +355,13 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
             if constexpr (M::EY) { o.x = gf[4]; hpv_st4(s_go + (M::C_EY * T + tid) * 4, o); }
         }
 #pragma unroll
-        for (int j = 0; j < HP; ++j) {
-            const float w = Wo[j];
-            g.v.a[j] = gf[0] * w;
-            if constexpr (M::DX) g.dx.a[j] = gf[1] * w;
-            if constexpr (M::DY) g.dy.a[j] = gf[2] * w;
-            if constexpr (M::EX) g.ex.a[j] = gf[3] * w;
-            if constexpr (M::EY) g.ey.a[j] = gf[4] * w;
+        for (int m = 0; m < HP / 2; ++m) {
+            const hpv_pair w = hpv_pack(Wo[2 * m], Wo[2 * m + 1]);
+            g.v.p[m] = hpv_mul2(hpv_dup(gf[0]), w);
+            if constexpr (M::DX) g.dx.p[m] = hpv_mul2(hpv_dup(gf[1]), w);
+            if constexpr (M::DY) g.dy.p[m] = hpv_mul2(hpv_dup(gf[2]), w);
+            if constexpr (M::EX) g.ex.p[m] = hpv_mul2(hpv_dup(gf[3]), w);
+            if constexpr (M::EY) g.ey.p[m] = hpv_mul2(hpv_dup(gf[4]), w);
         }
         hpv_sync(c);
         hpv_wgrad_gemm<SP, 4, M::NCH, HP, 1, true, 1, HP, DIM>(c, X, s_go, s_gw + hpv_off_wo(DIM, HP, nhid),
