@@ -37,13 +37,35 @@ def test_poisson2d_driver_defaults_train(capsys):
     # RHS produced by the reference driver == the engine-side assembly of the same quantity (sanity of layout)
     X, W = O.GaussLobattoJacobiWeights(10, 0, 0)
     assert np.allclose(O.rhs_2d_factorised(d["grid_x"], d["grid_y"], 5, 5, X, W), d["F_ext_total"], rtol=1e-10, atol=1e-12)
-    e0 = np.linalg.norm(model.predict() - u_test) / np.linalg.norm(u_test)
-    model.train(1500)
+    # the same optimisation in float64 on the CPU (factorised oracle + TF1-Adam restatement), same initial weights
+    import torch
+    theta = np.concatenate([np.concatenate([W.ravel(), b.ravel()]) for W, b in zip(model.weights, model.biases)])
+    layers = [int(v) for v in d["layers"]]
+    Xb, ub = d["X_u_train"], d["u_train"]
+
+    def total(Wt, bt):
+        lv = O.varloss_2d_factorised(Wt, bt, X, W, d["F_ext_total"], d["grid_x"], d["grid_y"], 5, 5, 1)[0]
+        return lv + 10 * O.lossb(Wt, bt, Xb, ub, "tanh")
+
+    n_it = 150
+    th, m_, v_ = theta.copy(), np.zeros_like(theta), np.zeros_like(theta)
+    ref_after = []
+    for t in range(1, n_it + 1):
+        Ws, bs = O.unpack_theta(th, layers)
+        _, g = O.loss_and_grad(total, Ws, bs)
+        th, m_, v_ = O.adam_tf1_step(th, g, m_, v_, t)
+        Ws, bs = O.unpack_theta(th, layers)
+        ref_after.append(float(total([torch.as_tensor(w_) for w_ in Ws], [torch.as_tensor(b_) for b_ in bs])))
+    model.train(n_it)
     out = capsys.readouterr().out
-    assert "It: 0, Loss:" in out and "It: 1400, Loss:" in out
-    assert len(loss_his) == 1500 and loss_his[-1] < 0.2 * loss_his[0]
-    e1 = np.linalg.norm(model.predict() - u_test) / np.linalg.norm(u_test)
-    assert e1 < 0.6 * e0
+    assert "It: 0, Loss:" in out and "It: 100, Loss:" in out
+    assert len(loss_his) == n_it
+    assert np.allclose(loss_his, ref_after, rtol=2e-3)                 # 150 fp32 GPU steps track the float64 path
+    assert loss_his[-1] < loss_his[0]
+    theta_gpu = np.concatenate([np.concatenate([W_.ravel(), b_.ravel()]) for W_, b_ in zip(model.weights, model.biases)])
+    assert np.abs(theta_gpu - th).max() < 2e-3
+    u_ref = O.neural_net(torch.as_tensor(X_test), *[[torch.as_tensor(t_) for t_ in part] for part in O.unpack_theta(th, layers)], "tanh")
+    assert np.abs(model.predict() - u_ref.numpy()).max() < 5e-3
     model.sess.close()
 
 
