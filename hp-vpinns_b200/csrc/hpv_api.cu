@@ -56,7 +56,7 @@ struct hpv_ctx {
     // parameters / optimiser
     DevBuf<float> theta_pad, eps;
     DevBuf<double> master, adam_m, adam_v, grad_out;
-    DevBuf<int> pad_index, step;
+    DevBuf<int> pad_index, pad_index2, step;
     // quadrature / tables
     DevBuf<float> xi1, tab[HPV_NTAB], tabN[HPV_NTAB];
     // elements
@@ -419,7 +419,7 @@ int hpv_create(hpv_ctx** out, int device) {
     if (prop.major != 10) return fail(c, HPV_ERR_CUDA, "libhpv is built for sm_100a (B200) only");
     int slot = -1;
     for (int i = 0; i < HPV_CSLOTS; ++i) if (!g_slot_used[device & 15][i]) { slot = i; break; }
-    if (slot < 0) return fail(c, HPV_ERR_LIMIT, "too many live contexts on this device (constant-memory parameter slots: 3)");
+    if (slot < 0) return fail(c, HPV_ERR_LIMIT, "too many live contexts on this device (constant-memory parameter slots: 2)");
     hpv_ctx* ctx = new hpv_ctx();
     ctx->device = device; ctx->n_sm = prop.multiProcessorCount; ctx->cslot = slot;
     g_slot_used[device & 15][slot] = true;
@@ -439,7 +439,7 @@ void hpv_destroy(hpv_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->theta_pad.release(); c->eps.release(); c->master.release(); c->adam_m.release(); c->adam_v.release();
-    c->grad_out.release(); c->pad_index.release(); c->step.release(); c->xi1.release();
+    c->grad_out.release(); c->pad_index.release(); c->pad_index2.release(); c->step.release(); c->xi1.release();
     for (int t = 0; t < HPV_NTAB; ++t) { c->tab[t].release(); c->tabN[t].release(); }
     c->geom.release(); c->F.release(); c->Res.release(); c->el_loss.release(); c->Upart.release(); c->Gbar.release();
     c->ntest.release(); c->cta_tile_begin.release(); c->el_first_cta.release(); c->el_part_off.release();
@@ -476,7 +476,7 @@ int hpv_set_network(hpv_ctx* c, int dim, const int* layers, int n_layers, int ac
     std::string err;
     HpvNet net;
     if (!hpv_net_setup(net, dim, layers, n_layers, act, err)) return fail(c, HPV_ERR_ARG, err);
-    if (net.theta_pad_n > HPV_CTHETA_MAX) return fail(c, HPV_ERR_LIMIT, "network too large for the constant-memory parameter slot (4096 padded floats)");
+    if (net.theta_pad_n > HPV_CTHETA_MAX) return fail(c, HPV_ERR_LIMIT, "network too large for the constant-memory parameter slot (6144 padded floats incl. transposed copies)");
     c->net = net; c->have_net = true; c->ready = false;
     c->mirror[0] = c->mirror[1] = c->mirror[2] = nullptr;
     theta_changed(c);
@@ -490,6 +490,7 @@ int hpv_set_network(hpv_ctx* c, int dim, const int* layers, int n_layers, int ac
     HPV_CK(cudaMemsetAsync(c->master.p, 0, (P + 1) * sizeof(double), c->stream));
     HPV_CK(c->step.alloc(1));
     { int r = upload(c, c->pad_index, net.pad_index); if (r) return r; }
+    { int r = upload(c, c->pad_index2, net.pad_index2); if (r) return r; }
     for (int s = 0; s < HPV_MAX_POINT_SETS; ++s) c->ps[s].active = false;
     return hpv_reset_optimizer(c);
 }
@@ -638,7 +639,7 @@ int hpv_forward_async(hpv_ctx* c) {
 
 static int unpad_grad(hpv_ctx* c, int update) {
     HpvAdamArgs a; memset(&a, 0, sizeof(a));
-    a.grad_pad = c->redbuf.p; a.pad_index = c->pad_index.p; a.n_theta = c->net.n_theta; a.theta_pad_n = c->net.theta_pad_n;
+    a.grad_pad = c->redbuf.p; a.pad_index = c->pad_index.p; a.pad_index2 = c->pad_index2.p; a.n_theta = c->net.n_theta; a.theta_pad_n = c->net.theta_pad_n;
     a.theta = c->master.p; a.m = c->adam_m.p; a.v = c->adam_v.p; a.theta_pad = c->theta_pad.p; a.eps = c->eps.p;
     a.grad_out = c->grad_out.p; a.train_eps = c->train_eps;
     a.lr = (float)c->lr; a.b1 = (float)c->b1; a.b2 = (float)c->b2; a.eps_hat = (float)c->eps_hat;

@@ -13,6 +13,7 @@ struct HpvNet {
     int dim = 0, nhid = 0, hp = 0, act = 0, n_theta = 0, theta_pad_n = 0;
     std::vector<int> layers;
     std::vector<int> pad_index;        // reference order (per layer: W row-major [in][out], then b) -> padded index
+    std::vector<int> pad_index2;       // second padded location of the same parameter (transposed copy) or -1
 };
 
 inline bool hpv_net_setup(HpvNet& n, int dim, const int* layers, int n_layers, int act, std::string& err) {
@@ -33,6 +34,7 @@ inline bool hpv_net_setup(HpvNet& n, int dim, const int* layers, int n_layers, i
     n.layers.assign(layers, layers + n_layers);
     n.theta_pad_n = hpv_theta_pad_n(dim, hp, nhid);
     n.pad_index.clear();
+    n.pad_index2.clear();
     for (int l = 0; l < n_layers - 1; ++l) {
         const int in = layers[l], out = layers[l + 1];
         int offW, offb, stride;
@@ -40,8 +42,11 @@ inline bool hpv_net_setup(HpvNet& n, int dim, const int* layers, int n_layers, i
         else if (l < nhid) { offW = hpv_off_wl(dim, hp, l); offb = offW + hp * hp; stride = hp; }
         else { offW = hpv_off_wo(dim, hp, nhid); offb = offW + hp; stride = 1; }
         for (int i = 0; i < in; ++i)
-            for (int j = 0; j < out; ++j) n.pad_index.push_back(offW + i * stride + j);
-        for (int j = 0; j < out; ++j) n.pad_index.push_back(offb + j);
+            for (int j = 0; j < out; ++j) {
+                n.pad_index.push_back(offW + i * stride + j);
+                n.pad_index2.push_back((l >= 1 && l < nhid) ? hpv_off_wt(dim, hp, nhid, l) + j * hp + i : -1);
+            }
+        for (int j = 0; j < out; ++j) { n.pad_index.push_back(offb + j); n.pad_index2.push_back(-1); }
     }
     n.n_theta = (int)n.pad_index.size();
     return true;
@@ -49,7 +54,10 @@ inline bool hpv_net_setup(HpvNet& n, int dim, const int* layers, int n_layers, i
 
 inline void hpv_pad_theta(const HpvNet& n, const double* theta, std::vector<float>& out) {
     out.assign(n.theta_pad_n, 0.0f);
-    for (int i = 0; i < n.n_theta; ++i) out[n.pad_index[i]] = (float)theta[i];
+    for (int i = 0; i < n.n_theta; ++i) {
+        out[n.pad_index[i]] = (float)theta[i];
+        if (n.pad_index2[i] >= 0) out[n.pad_index2[i]] = (float)theta[i];
+    }
 }
 
 // Instantiated derivative modes: 1-D (mx); 2-D (0,0), (1,1), (2,1), (2,2).

@@ -60,7 +60,11 @@ __global__ void hpv_adam_kernel(const HpvAdamArgs a) {
     const double th = d.theta[i] - lr_t * m / (sqrt(v) + (double)a.eps_hat);
     d.m[i] = m; d.v[i] = v; d.theta[i] = th;
     if (is_eps) a.eps[0] = (float)th;
-    else a.theta_pad[a.pad_index[i]] = (float)th;
+    else {
+        a.theta_pad[a.pad_index[i]] = (float)th;
+        const int i2 = a.pad_index2[i];
+        if (i2 >= 0) a.theta_pad[i2] = (float)th;
+    }
 }
 
 __global__ void hpv_step_inc_kernel(int* step) { step[0] += 1; }

@@ -52,6 +52,7 @@ cudaError_t hpv_launch_gradreduce(const HpvGradReduceArgs& a, cudaStream_t s);
 struct HpvAdamArgs {
     const float* grad_pad;     // padded gradient (+ d eps at index theta_pad_n)
     const int* pad_index;      // [n_theta] reference-order index -> padded index
+    const int* pad_index2;     // [n_theta] second padded location (transposed copy) or -1
     int n_theta, theta_pad_n;
     double* theta;             // [n_theta + 1] float64 master parameters, reference order, eps last
     double* m; double* v;      // Adam moments, same layout

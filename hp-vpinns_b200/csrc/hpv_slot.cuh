@@ -70,7 +70,8 @@ HPV_HD void hpv_load_state(const float* slot, int T, int tid, HpvState<DIM, MX, 
 }
 
 // out = in . W (+ b on the value channel), inputs read from this thread's slot rows, outputs in registers.
-template <int DIM, int MX, int MY, int HP>
+// BIAS = false (b unused) gives the plain product, used with the transposed weights for the adjoint sweep.
+template <int DIM, int MX, int MY, int HP, bool BIAS = true>
 HPV_HD void hpv_matmul_slot(const float* W, const float* b, const float* slot, int T, int tid,
                             HpvState<DIM, MX, MY, HP>& out) {
     typedef HpvMode<DIM, MX, MY> M;
@@ -78,7 +79,7 @@ HPV_HD void hpv_matmul_slot(const float* W, const float* b, const float* slot, i
     hpv_pair acc[NCH][HP / 2];
 #pragma unroll
     for (int m = 0; m < HP / 2; ++m) {
-        acc[0][m] = hpv_pack(b[2 * m], b[2 * m + 1]);
+        acc[0][m] = BIAS ? hpv_pack(b[2 * m], b[2 * m + 1]) : hpv_dup(0.0f);
 #pragma unroll
         for (int c = 1; c < NCH; ++c) acc[c][m] = hpv_dup(0.0f);
     }
@@ -109,45 +110,6 @@ HPV_HD void hpv_matmul_slot(const float* W, const float* b, const float* slot, i
 #pragma unroll
         for (int m = 0; m < HP / 2; ++m) a[m] = acc[c][m];
     });
-}
-
-// Transposed product of the reverse sweep: out[i] = sum_j in[j] W[i][j] for every channel; inputs in registers,
-// outputs written to this thread's slot rows (which may be the rows the inputs were loaded from).
-template <int DIM, int MX, int MY, int HP>
-HPV_HD void hpv_matmul_t_slot(const float* W, const HpvState<DIM, MX, MY, HP>& in, float* slot, int T, int tid) {
-    typedef HpvMode<DIM, MX, MY> M;
-    constexpr int SP = HpvSP<HP>::value, NCH = M::NCH;
-    const hpv_pair* inp[NCH];
-    hpv_each_ch<M>(in, [&](const hpv_pair* a, int c) { inp[c] = a; });
-    float* row = slot + (size_t)tid * SP;
-#pragma unroll 1
-    for (int i4 = 0; i4 < HP / 4; ++i4) {
-        float o[NCH][4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float* wr = W + (4 * i4 + k) * HP;
-            hpv_pair s[NCH];
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) s[c] = hpv_dup(0.0f);
-#pragma unroll
-            for (int m = 0; m < HP / 2; ++m) {
-                const hpv_pair w = hpv_pack(wr[2 * m], wr[2 * m + 1]);
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) hpv_fma2(s[c], inp[c][m], w);
-            }
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                float lo, hi;
-                hpv_unpack(s[c], lo, hi);
-                o[c][k] = lo + hi;
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            HpvF4 v; v.x = o[c][0]; v.y = o[c][1]; v.z = o[c][2]; v.w = o[c][3];
-            hpv_st4(row + (size_t)c * T * SP + 4 * i4, v);
-        }
-    }
 }
 
 // Output layer from the slot: fields (u, u_x, u_y, u_xx, u_yy); absent ones are 0.

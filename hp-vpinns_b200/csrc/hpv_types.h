@@ -11,8 +11,8 @@
 #define HPV_MAX_HIDDEN 8       // hidden layers
 #define HPV_QMAX 128           // quadrature points per direction
 #define HPV_NTAB 4             // T*w, D1*w, D2*w, ONE
-#define HPV_CSLOTS 3            // contexts per device whose parameters can be resident in constant memory
-#define HPV_CTHETA_MAX 4096     // floats of padded parameters per context (16 KB)
+#define HPV_CSLOTS 2            // contexts per device whose parameters can be resident in constant memory
+#define HPV_CTHETA_MAX 6144     // floats of padded parameters (incl. transposed copies) per context (24 KB)
 
 // One projected term:  U += s * Jx^px * Jy^py * (L-table) . G . (R-table)^T,
 // with the point field  G = sum_f (a0[f] + eps*a1[f]) * field_f  (field order above).

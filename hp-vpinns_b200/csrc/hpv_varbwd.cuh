@@ -194,19 +194,23 @@ HPV_HD void hpv_wgrad_gemm(const HpvCta& c, const float* IN, const float* ADJ, f
     if (active) {
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
-            const float* inb = IN + (size_t)ch * T * SPI;
-            const float* adb = ADJ + (size_t)ch * T * SPA + 4 * jt;
+            const float* pa0 = IN + (size_t)ch * T * SPI + ks * SPI + r0;
+            const float* pa1 = pa0 + 4;
+            const float* pb = ADJ + (size_t)ch * T * SPA + ks * SPA + 4 * jt;
+            const int sa = KS * SPI, sb = KS * SPA;
             const float one = (ch == 0) ? 1.0f : 0.0f;
-#pragma unroll 2
-            for (int p = ks; p < T; p += KS) {
+            const int niter = (T - ks + KS - 1) / KS;
+#pragma unroll 4
+            for (int it2 = 0; it2 < niter; ++it2) {
                 HpvF4 a0, a1;
                 a0.x = one; a0.y = a0.z = a0.w = 0.0f;
                 a1 = a0;
-                if (ty0 == 0) a0 = hpv_ld4(inb + p * SPI + r0);
+                if (ty0 == 0) a0 = hpv_ld4(pa0);
                 else if (ty0 == 2) a0.x = 0.0f;
-                if (ty1 == 0) a1 = hpv_ld4(inb + p * SPI + r1);
+                if (ty1 == 0) a1 = hpv_ld4(pa1);
                 else if (ty1 == 2) a1.x = 0.0f;
-                const HpvF4 b4 = hpv_ld4(adb + p * SPA);
+                const HpvF4 b4 = hpv_ld4(pb);
+                pa0 += sa; pa1 += sa; pb += sb;
                 const hpv_pair b01 = hpv_pack(b4.x, b4.y), b23 = hpv_pack(b4.z, b4.w);
                 const float as[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
@@ -385,8 +389,8 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
             float* gW = s_gw + hpv_off_wl(DIM, HP, l);
             hpv_wgrad_gemm<SP, SP, M::NCH, HP, HP / 4, true, 0, HP, DIM>(c, INl, X, gW, gW + HP * HP, s_scr);
             hpv_sync(c);
-            hpv_matmul_t_slot<DIM, MX, MY, HP>(s_th + hpv_off_wl(DIM, HP, l), g, X, T, tid);   // adjoint of h_{l-1}, in place
-            hpv_load_state<DIM, MX, MY, HP>(X, T, tid, g);
+            // adjoint of h_{l-1} = ADJ_l . W_l^T: the forward product loop on the transposed copy, inputs from X
+            hpv_matmul_slot<DIM, MX, MY, HP, false>(s_th + hpv_off_wt(DIM, HP, nhid, l), nullptr, X, T, tid, g);
         }
 
         // ---- first layer ----
