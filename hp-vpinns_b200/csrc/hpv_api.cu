@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <stdint.h>
 #include <string>
 #include <vector>
@@ -77,14 +78,15 @@ struct hpv_ctx {
     std::vector<float> host_f32;
     std::vector<double> host_f64;
     // constant-memory mirrors of theta_pad, one per kernel translation unit kind (forward, reverse sweep, points)
-    int cslot = -1;
     float* mirror[3] = {nullptr, nullptr, nullptr};
     bool mirror_stale[3] = {true, true, true};
 };
 
 namespace {
 
-bool g_slot_used[16][HPV_CSLOTS];
+// Which context's parameters each constant-memory copy (device x padded width x kernel kind) holds right now.
+std::mutex g_owner_mutex;
+hpv_ctx* g_owner[16][3][3];
 
 int fail(hpv_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg; else g_create_error = msg;
@@ -120,7 +122,16 @@ int refresh_mirror(hpv_ctx* c, int kind) {
         long long out = 0;
         l.kind = kind; l.op = 3; l.out = &out;
         HPV_CK(hpv_dispatch(key_of(c, 0, 0), l));
-        c->mirror[kind] = reinterpret_cast<float*>((uintptr_t)out) + (size_t)c->cslot * HPV_CTHETA_MAX;
+        c->mirror[kind] = reinterpret_cast<float*>((uintptr_t)out);
+        c->mirror_stale[kind] = true;
+    }
+    std::lock_guard<std::mutex> lock(g_owner_mutex);
+    const int hpi = c->net.hp == 8 ? 0 : (c->net.hp == 20 ? 1 : 2);
+    hpv_ctx*& owner = g_owner[c->device & 15][hpi][kind];
+    if (owner != c) {
+        // another context's kernels may still be reading this copy: let them finish before overwriting it
+        if (owner && owner->stream != c->stream) HPV_CK(cudaStreamSynchronize(owner->stream));
+        owner = c;
         c->mirror_stale[kind] = true;
     }
     if (c->mirror_stale[kind]) {
@@ -135,7 +146,8 @@ void theta_changed(hpv_ctx* c) { c->mirror_stale[0] = c->mirror_stale[1] = c->mi
 void fill_var_args(hpv_ctx* c, HpvVarArgs& a) {
     memset(&a, 0, sizeof(a));
     a.theta_pad = c->theta_pad.p; a.theta_pad_n = c->net.theta_pad_n; a.nhid = c->net.nhid; a.eps = c->eps.p;
-    a.cslot = c->cslot;
+    a.off_wo = hpv_off_wo(c->net.dim, c->net.hp, c->net.nhid);
+
     a.Q = c->Q; a.rows = (c->net.dim == 2) ? c->Q : 1; a.xi1 = c->xi1.p;
     for (int t = 0; t < HPV_NTAB; ++t) { a.tab[t] = c->tab[t].p; a.tabN[t] = c->tabN[t].p; }
     a.QP = hpv_align4(c->Q);
@@ -157,7 +169,7 @@ void fill_var_args(hpv_ctx* c, HpvVarArgs& a) {
 int plan_bwd(hpv_ctx* c, int mx, int my, int& block, int& ctas_per_sm, size_t& smem) {
     const HpvKernelKey k = key_of(c, mx, my);
     HpvVarArgs va; memset(&va, 0, sizeof(va));
-    va.theta_pad_n = c->net.theta_pad_n; va.nhid = c->net.nhid;
+    va.theta_pad_n = c->net.theta_pad_n; va.nhid = c->net.nhid; va.off_wo = hpv_off_wo(c->net.dim, c->net.hp, c->net.nhid);
     HpvBwdArgs ba; memset(&ba, 0, sizeof(ba)); ba.v = va;
     int best_threads = 0;
     int cand[3] = {128, 256, 64};
@@ -308,7 +320,8 @@ int launch_points(hpv_ctx* c, int mx, int my, int n, const float* pts, float* u,
     { int r = refresh_mirror(c, HPV_K_POINTS); if (r) return r; }
     HpvPointArgs p; memset(&p, 0, sizeof(p));
     p.theta_pad = c->theta_pad.p; p.theta_pad_n = c->net.theta_pad_n; p.nhid = c->net.nhid; p.eps = c->eps.p;
-    p.cslot = c->cslot;
+    p.off_wo = hpv_off_wo(c->net.dim, c->net.hp, c->net.nhid);
+
     p.n = n; p.pts = pts; p.out_u = u; p.out_d1 = d1; p.out_d2 = d2;
     int grid = (n + HPV_THREADS - 1) / HPV_THREADS;
     if (grid > c->n_sm * 4) grid = c->n_sm * 4;
@@ -340,7 +353,8 @@ int launch_mlpbwd_points(hpv_ctx* c, PointSet& ps, int& grid_out) {
     HpvBwdArgs ba; memset(&ba, 0, sizeof(ba));
     HpvVarArgs& a = ba.v;
     a.theta_pad = c->theta_pad.p; a.theta_pad_n = c->net.theta_pad_n; a.nhid = c->net.nhid; a.eps = c->eps.p;
-    a.cslot = c->cslot;
+    a.off_wo = hpv_off_wo(c->net.dim, c->net.hp, c->net.nhid);
+
     a.Q = 1; a.rows = 1; a.n_terms = 1;
     a.terms[0] = hpv_term_zero();
     for (int f = 0; f < HPV_NFIELDS; ++f) { a.terms[0].a0[f] = ps.a0[f]; a.terms[0].a1[f] = ps.a1[f]; }
@@ -417,15 +431,10 @@ int hpv_create(hpv_ctx** out, int device) {
     e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) return fail(c, HPV_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
     if (prop.major != 10) return fail(c, HPV_ERR_CUDA, "libhpv is built for sm_100a (B200) only");
-    int slot = -1;
-    for (int i = 0; i < HPV_CSLOTS; ++i) if (!g_slot_used[device & 15][i]) { slot = i; break; }
-    if (slot < 0) return fail(c, HPV_ERR_LIMIT, "too many live contexts on this device (constant-memory parameter slots: 2)");
     hpv_ctx* ctx = new hpv_ctx();
-    ctx->device = device; ctx->n_sm = prop.multiProcessorCount; ctx->cslot = slot;
-    g_slot_used[device & 15][slot] = true;
+    ctx->device = device; ctx->n_sm = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
-        g_slot_used[device & 15][slot] = false;
         delete ctx;
         return fail(c, HPV_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     }
@@ -449,7 +458,10 @@ void hpv_destroy(hpv_ctx* c) {
         c->ps[s].blk_loss.release();
     }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
-    if (c->cslot >= 0) g_slot_used[c->device & 15][c->cslot] = false;
+    {
+        std::lock_guard<std::mutex> lock(g_owner_mutex);
+        for (int h = 0; h < 3; ++h) for (int k = 0; k < 3; ++k) if (g_owner[c->device & 15][h][k] == c) g_owner[c->device & 15][h][k] = nullptr;
+    }
     delete c;
 }
 
@@ -476,7 +488,7 @@ int hpv_set_network(hpv_ctx* c, int dim, const int* layers, int n_layers, int ac
     std::string err;
     HpvNet net;
     if (!hpv_net_setup(net, dim, layers, n_layers, act, err)) return fail(c, HPV_ERR_ARG, err);
-    if (net.theta_pad_n > HPV_CTHETA_MAX) return fail(c, HPV_ERR_LIMIT, "network too large for the constant-memory parameter slot (6144 padded floats incl. transposed copies)");
+    if (net.theta_pad_n > HPV_CTHETA_MAX) return fail(c, HPV_ERR_LIMIT, "network too large for the constant-memory parameter mirror (12288 padded floats incl. transposed copies)");
     c->net = net; c->have_net = true; c->ready = false;
     c->mirror[0] = c->mirror[1] = c->mirror[2] = nullptr;
     theta_changed(c);

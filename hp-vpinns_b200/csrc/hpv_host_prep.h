@@ -44,7 +44,7 @@ inline bool hpv_net_setup(HpvNet& n, int dim, const int* layers, int n_layers, i
         for (int i = 0; i < in; ++i)
             for (int j = 0; j < out; ++j) {
                 n.pad_index.push_back(offW + i * stride + j);
-                n.pad_index2.push_back((l >= 1 && l < nhid) ? hpv_off_wt(dim, hp, nhid, l) + j * hp + i : -1);
+                n.pad_index2.push_back((l >= 1 && l < nhid) ? hpv_off_wt(dim, hp, l) + j * hp + i : -1);
             }
         for (int j = 0; j < out; ++j) { n.pad_index.push_back(offb + j); n.pad_index2.push_back(-1); }
     }

@@ -16,17 +16,18 @@ HPV_HD HpvF4 hpv_ld4(const float* p) { return *reinterpret_cast<const HpvF4*>(p)
 HPV_HD void hpv_st4(float* p, const HpvF4& v) { *reinterpret_cast<HpvF4*>(p) = v; }
 
 // ---- padded parameter layout --------------------------------------------------------------------------
-// [W1: DIM x HP][b1: HP] { [W_l: HP x HP][b_l: HP] } x (nhid-1) [Wo: HP][bo, 0, 0, 0] { [W_l^T: HP x HP] } x (nhid-1)
-// The transposed copies at the end serve the adjoint product of the reverse sweep (out[i] = sum_j in[j] W[i][j]),
-// which then runs as the same broadcast-input / uniform-weight FFMA2 loop as the forward product.
+// [W1: DIM x HP][b1: HP] { [W_l: HP x HP][b_l: HP][W_l^T: HP x HP] } x (nhid-1) [Wo: HP][bo, 0, 0, 0]
+// The transposed copy of each hidden matrix serves the adjoint product of the reverse sweep
+// (out[i] = sum_j in[j] W[i][j]), which then runs as the same broadcast-input / uniform-weight FFMA2 loop as
+// the forward product.  Hidden-layer offsets depend on the layer index only (they stay in uniform registers).
 // Hidden width H is zero-padded to HP: a padded unit has z = 0 -> sigma(0) = 0 for both sin and tanh and
 // all its tangents are 0, so the padding is exact.
 HPV_HD int hpv_off_w1() { return 0; }
 HPV_HD int hpv_off_b1(int dim, int hp) { return dim * hp; }
-HPV_HD int hpv_off_wl(int dim, int hp, int l /*1..nhid-1*/) { return (dim + 1) * hp + (l - 1) * (hp * hp + hp); }
-HPV_HD int hpv_off_wo(int dim, int hp, int nhid) { return (dim + 1) * hp + (nhid - 1) * (hp * hp + hp); }
-HPV_HD int hpv_off_wt(int dim, int hp, int nhid, int l /*1..nhid-1*/) { return hpv_off_wo(dim, hp, nhid) + hp + 4 + (l - 1) * hp * hp; }
-HPV_HD int hpv_theta_pad_n(int dim, int hp, int nhid) { return hpv_off_wo(dim, hp, nhid) + hp + 4 + (nhid - 1) * hp * hp; }
+HPV_HD int hpv_off_wl(int dim, int hp, int l /*1..nhid-1*/) { return (dim + 1) * hp + (l - 1) * (2 * hp * hp + hp); }
+HPV_HD int hpv_off_wt(int dim, int hp, int l /*1..nhid-1*/) { return hpv_off_wl(dim, hp, l) + hp * hp + hp; }
+HPV_HD int hpv_off_wo(int dim, int hp, int nhid) { return (dim + 1) * hp + (nhid - 1) * (2 * hp * hp + hp); }
+HPV_HD int hpv_theta_pad_n(int dim, int hp, int nhid) { return hpv_off_wo(dim, hp, nhid) + hp + 4; }
 
 // ---- activations ----------------------------------------------------------------------------------------
 // tanh as 1 - 2/(exp(2z)+1): absolute error ~1e-7 (what matters: the value feeds dot products), saturates

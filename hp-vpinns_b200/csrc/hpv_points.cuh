@@ -15,7 +15,7 @@ HPV_HD void hpv_points_body(const HpvCta& c, const HpvPointArgs& a, float* gbar_
     float* s_red = sm;
     const int T = c.nthreads, tid = c.tid;
     float* s_slot = sm + T;
-    const float* th = HPV_THETA(a.theta_pad, a.cslot);
+    const float* th = HPV_THETA(a.theta_pad);
     const float eps = a.eps[0];
     float cf[HPV_NFIELDS];
     for (int k = 0; k < HPV_NFIELDS; ++k) cf[k] = fmaf(eps, a.a1[k], a.a0[k]);
@@ -27,7 +27,7 @@ HPV_HD void hpv_points_body(const HpvCta& c, const HpvPointArgs& a, float* gbar_
             const float x = a.pts[(size_t)i * DIM];
             const float y = (DIM == 2) ? a.pts[(size_t)i * DIM + 1] : 0.0f;
             float f[HPV_NFIELDS];
-            hpv_net_point_slot<DIM, MX, MY, HP, ACT>(th, a.nhid, x, y, s_slot, T, tid, f);
+            hpv_net_point_slot<DIM, MX, MY, HP, ACT>(th, a.nhid, a.off_wo, x, y, s_slot, T, tid, f);
             if (a.out_u) a.out_u[i] = f[0];
             if (a.out_d1) { a.out_d1[(size_t)i * DIM] = f[1]; if (DIM == 2) a.out_d1[(size_t)i * DIM + 1] = f[2]; }
             if (a.out_d2) { a.out_d2[(size_t)i * DIM] = f[3]; if (DIM == 2) a.out_d2[(size_t)i * DIM + 1] = f[4]; }

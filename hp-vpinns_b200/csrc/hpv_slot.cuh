@@ -83,18 +83,21 @@ HPV_HD void hpv_matmul_slot(const float* W, const float* b, const float* slot, i
 #pragma unroll
         for (int c = 1; c < NCH; ++c) acc[c][m] = hpv_dup(0.0f);
     }
+    // two independent induction variables: the weight pointer (constant memory, must stay in uniform registers so
+    // that the loads are LDCU and the FFMA2 take a UR operand) and the slot-row pointer (per-thread, vector)
     const float* row = slot + (size_t)tid * SP;
+    const float* wr0 = W;
 #pragma unroll 1
-    for (int i4 = 0; i4 < HP / 4; ++i4) {
+    for (int i4 = 0; i4 < HP / 4; ++i4, row += 4, wr0 += 4 * HP) {
         float x[NCH][4];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-            const HpvF4 v = hpv_ld4(row + (size_t)c * T * SP + 4 * i4);
+            const HpvF4 v = hpv_ld4(row + (size_t)c * T * SP);
             x[c][0] = v.x; x[c][1] = v.y; x[c][2] = v.z; x[c][3] = v.w;
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float* wr = W + (4 * i4 + k) * HP;
+            const float* wr = wr0 + k * HP;
             hpv_pair xd[NCH];
 #pragma unroll
             for (int c = 0; c < NCH; ++c) xd[c] = hpv_dup(x[c][k]);
@@ -140,7 +143,7 @@ HPV_HD void hpv_output_slot(const float* Wo, const float* slot, int T, int tid, 
 
 // Whole network at one point through a slot (the forward kernel's inner loop).
 template <int DIM, int MX, int MY, int HP, int ACT>
-HPV_HD void hpv_net_point_slot(const float* th, int nhid, float x, float y, float* slot, int T, int tid,
+HPV_HD void hpv_net_point_slot(const float* th, int nhid, int off_wo, float x, float y, float* slot, int T, int tid,
                                float f[HPV_NFIELDS]) {
     HpvState<DIM, MX, MY, HP> s;
     hpv_layer1_pre<DIM, MX, MY, HP>(th, x, y, s);
@@ -153,5 +156,5 @@ HPV_HD void hpv_net_point_slot(const float* th, int nhid, float x, float y, floa
         hpv_activate<DIM, MX, MY, HP, ACT>(s);
         hpv_store_state<DIM, MX, MY, HP>(slot, T, tid, s);
     }
-    hpv_output_slot<DIM, MX, MY, HP>(th + hpv_off_wo(DIM, HP, nhid), slot, T, tid, f);
+    hpv_output_slot<DIM, MX, MY, HP>(th + off_wo, slot, T, tid, f);
 }

@@ -11,8 +11,7 @@
 #define HPV_MAX_HIDDEN 8       // hidden layers
 #define HPV_QMAX 128           // quadrature points per direction
 #define HPV_NTAB 4             // T*w, D1*w, D2*w, ONE
-#define HPV_CSLOTS 2            // contexts per device whose parameters can be resident in constant memory
-#define HPV_CTHETA_MAX 6144     // floats of padded parameters (incl. transposed copies) per context (24 KB)
+#define HPV_CTHETA_MAX 12288    // floats of padded parameters (incl. transposed copies) in constant memory (48 KB)
 
 // One projected term:  U += s * Jx^px * Jy^py * (L-table) . G . (R-table)^T,
 // with the point field  G = sum_f (a0[f] + eps*a1[f]) * field_f  (field order above).
@@ -27,10 +26,10 @@ struct HpvTerm {
 // Arguments of the fused variational kernels (forward: residual + loss; backward: d loss / d theta, d eps).
 struct HpvVarArgs {
     // network (padded layout, see hpv_host_prep.h)
-    const float* theta_pad;    // global copy (host emulation; on the device the kernels read constant slot `cslot`)
+    const float* theta_pad;    // global copy (host emulation; on the device the kernels read the constant-memory mirror)
     int theta_pad_n;
-    int cslot;
     int nhid;                  // number of hidden layers
+    int off_wo;                // offset of the output layer in the padded layout (hpv_off_wo)
     const float* eps;          // device scalar (AdvDiff diffusivity), never null
     // quadrature and test-function tables
     int Q;                     // nodes per direction
@@ -74,8 +73,8 @@ struct HpvVarArgs {
 struct HpvPointArgs {
     const float* theta_pad;
     int theta_pad_n;
-    int cslot;
     int nhid;
+    int off_wo;
     const float* eps;
     int n;
     const float* pts;          // [n][dim]

@@ -269,7 +269,7 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
     const int T = c.nthreads, tid = c.tid, nhid = a.nhid, top = nhid - 1;
     const HpvBwdSmem<DIM, MX, MY, HP> L(a.theta_pad_n, nhid, T);
     float* sm = reinterpret_cast<float*>(c.smem);
-    const float* s_th = HPV_THETA(a.theta_pad, a.cslot);
+    const float* s_th = HPV_THETA(a.theta_pad);
     float* s_gw = sm + L.gw;
     float* s_in0 = sm + L.in0;
     float* s_go = sm + L.go;
@@ -298,7 +298,7 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
     float deps = 0.0f;
     const int tile_begin = (int)(((long long)c.bid * ba.n_tiles) / c.nblocks);
     const int tile_end = (int)(((long long)(c.bid + 1) * ba.n_tiles) / c.nblocks);
-    const float* Wo = s_th + hpv_off_wo(DIM, HP, nhid);
+    const float* Wo = s_th + a.off_wo;
 
 #pragma unroll 1
     for (int tile = tile_begin; tile < tile_end; ++tile) {
@@ -322,11 +322,12 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
         // ---- forward recompute; the pre-activations of hidden layers 1..top-1 stay in their slots ----
         State pre, g;
         hpv_layer1_pre<DIM, MX, MY, HP>(s_th, x, y, pre);
+        int woff = hpv_off_wl(DIM, HP, 1);                           // constant-memory offsets: own induction variables
 #pragma unroll 1
-        for (int l = 1; l <= top; ++l) {
+        for (int l = 1; l <= top; ++l, woff += 2 * HP * HP + HP) {
             hpv_activate<DIM, MX, MY, HP, ACT>(pre);                     // h_{l-1}
             hpv_store_state<DIM, MX, MY, HP>(X, T, tid, pre);
-            const float* W = s_th + hpv_off_wl(DIM, HP, l);
+            const float* W = s_th + woff;
             hpv_matmul_slot<DIM, MX, MY, HP>(W, W + HP * HP, X, T, tid, pre);
             if (l < top) hpv_store_state<DIM, MX, MY, HP>(HPV_P(l), T, tid, pre);
         }
@@ -368,13 +369,14 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
             if constexpr (M::EY) g.ey.p[m] = hpv_mul2(hpv_dup(gf[4]), w);
         }
         hpv_sync(c);
-        hpv_wgrad_gemm<SP, 4, M::NCH, HP, 1, true, 1, HP, DIM>(c, X, s_go, s_gw + hpv_off_wo(DIM, HP, nhid),
-                                                                s_gw + hpv_off_wo(DIM, HP, nhid) + HP, s_scr);
+        hpv_wgrad_gemm<SP, 4, M::NCH, HP, 1, true, 1, HP, DIM>(c, X, s_go, s_gw + a.off_wo,
+                                                                s_gw + a.off_wo + HP, s_scr);
         hpv_sync(c);
 
         // ---- hidden layers, top down ----
+        int woff_t = a.off_wo - HP * HP;                             // = hpv_off_wt(DIM, HP, top)
 #pragma unroll 1
-        for (int l = top; l >= 1; --l) {
+        for (int l = top; l >= 1; --l, woff_t -= 2 * HP * HP + HP) {
             hpv_activate_bwd<DIM, MX, MY, HP, ACT>(pre, g);             // g := adjoint of the pre-activations of layer l
             hpv_store_state<DIM, MX, MY, HP>(X, T, tid, g);
             float* INl = (l - 1 >= 1) ? HPV_P(l - 1) : H0;
@@ -390,7 +392,7 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
             hpv_wgrad_gemm<SP, SP, M::NCH, HP, HP / 4, true, 0, HP, DIM>(c, INl, X, gW, gW + HP * HP, s_scr);
             hpv_sync(c);
             // adjoint of h_{l-1} = ADJ_l . W_l^T: the forward product loop on the transposed copy, inputs from X
-            hpv_matmul_slot<DIM, MX, MY, HP, false>(s_th + hpv_off_wt(DIM, HP, nhid, l), nullptr, X, T, tid, g);
+            hpv_matmul_slot<DIM, MX, MY, HP, false>(s_th + woff_t, nullptr, X, T, tid, g);
         }
 
         // ---- first layer ----

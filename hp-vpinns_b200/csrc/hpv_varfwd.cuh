@@ -65,7 +65,7 @@ HPV_HD void hpv_varfwd_body(const HpvCta& c, const HpvVarArgs& a) {
     const int T = c.nthreads, tid = c.tid;
     const HpvFwdSmem L = hpv_fwd_smem(a, HpvMode<DIM, MX, MY>::NCH * T * HpvSP<HP>::value);
     float* sm = reinterpret_cast<float*>(c.smem);
-    const float* th = HPV_THETA(a.theta_pad, a.cslot);
+    const float* th = HPV_THETA(a.theta_pad);
     float* s_xi1 = sm + L.xi1;
     float* s_G = sm + L.G;
     float* s_P = sm + L.P;
@@ -120,7 +120,7 @@ HPV_HD void hpv_varfwd_body(const HpvCta& c, const HpvVarArgs& a) {
                 const float x = fmaf(hwx, s_xi1[i], lox);
                 const float y = (DIM == 2) ? fmaf(hwy, s_xi1[j], loy) : 0.0f;
                 float f[HPV_NFIELDS];
-                hpv_net_point_slot<DIM, MX, MY, HP, ACT>(th, a.nhid, x, y, s_slot, T, tid, f);
+                hpv_net_point_slot<DIM, MX, MY, HP, ACT>(th, a.nhid, a.off_wo, x, y, s_slot, T, tid, f);
                 for (int t = 0; t < a.n_terms; ++t) {
                     float g = 0.0f;
 #pragma unroll

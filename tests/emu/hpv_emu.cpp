@@ -138,6 +138,7 @@ int hpv_emu_varloss(int dim, const int* layers, int n_layers, int act, int Q, co
     HpvVarArgs a;
     memset(&a, 0, sizeof(a));
     a.theta_pad = th.data(); a.theta_pad_n = net.theta_pad_n; a.nhid = net.nhid; a.eps = &epsf;
+    a.off_wo = hpv_off_wo(net.dim, net.hp, net.nhid);
     a.Q = Q; a.rows = rows; a.xi1 = xi1.data();
     for (int t = 0; t < HPV_NTAB; ++t) { a.tab[t] = tabs[t].data(); a.tabN[t] = nat[t].data(); }
     a.QP = hpv_align4(Q);
@@ -201,6 +202,7 @@ int hpv_emu_points(int dim, const int* layers, int n_layers, int act, const doub
     HpvPointArgs a;
     memset(&a, 0, sizeof(a));
     a.theta_pad = th.data(); a.theta_pad_n = net.theta_pad_n; a.nhid = net.nhid; a.eps = &epsf;
+    a.off_wo = hpv_off_wo(net.dim, net.hp, net.nhid);
     a.n = n; a.pts = p.data(); a.out_u = ou.data(); a.out_d1 = od1.data(); a.out_d2 = od2.data();
     int mx = mode, my = mode;
     if (target) {
@@ -228,6 +230,7 @@ int hpv_emu_points(int dim, const int* layers, int n_layers, int act, const doub
     HpvBwdArgs ba;
     memset(&ba, 0, sizeof(ba));
     ba.v.theta_pad = th.data(); ba.v.theta_pad_n = net.theta_pad_n; ba.v.nhid = net.nhid; ba.v.eps = &epsf;
+    ba.v.off_wo = hpv_off_wo(net.dim, net.hp, net.nhid);
     ba.v.Q = 1; ba.v.rows = 1; ba.v.n_terms = 1; ba.v.terms[0] = hpv_term_zero();
     for (int f = 0; f < HPV_NFIELDS; ++f) { ba.v.terms[0].a0[f] = a.a0[f]; ba.v.terms[0].a1[f] = a.a1[f]; }
     ba.v.grad_part = gpart.data(); ba.v.grad_stride = stride;
