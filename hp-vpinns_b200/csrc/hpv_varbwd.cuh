@@ -225,6 +225,9 @@ HPV_HD void hpv_wgrad_gemm(const HpvCta& c, const float* IN, const float* ADJ, f
     float out[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { hpv_unpack(acc[i][0], out[i][0], out[i][1]); hpv_unpack(acc[i][1], out[i][2], out[i][3]); }
+    // Combine the KS partial tiles through shared memory.  Every thread of a tile's group takes part: thread ks
+    // sums rows ks, ks+KS, ... of the 8-row tile over the KS partials in a fixed order (deterministic), and adds
+    // them to the accumulated gradient.
     if (KS > 1) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -232,29 +235,33 @@ HPV_HD void hpv_wgrad_gemm(const HpvCta& c, const float* IN, const float* ADJ, f
             hpv_st4(scratch + tid * 32 + 4 * i, o);
         }
         hpv_sync(c);
-        if (active && ks == 0) {
-            for (int s = 1; s < KS; ++s) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const HpvF4 v = hpv_ld4(scratch + (tid + s) * 32 + 4 * i);
-                    out[i][0] += v.x; out[i][1] += v.y; out[i][2] += v.z; out[i][3] += v.w;
-                }
-            }
-        }
     }
-    if (active && ks == 0) {
+    if (active) {
+        const float* grp = scratch + (size_t)(tid - ks) * 32;
+        for (int i = ks; i < 8; i += KS) {
+            float v[4];
+            if (KS > 1) {
+                HpvF4 s4 = hpv_ld4(grp + 4 * i);
+                for (int s = 1; s < KS; ++s) {
+                    const HpvF4 t4 = hpv_ld4(grp + s * 32 + 4 * i);
+                    s4.x += t4.x; s4.y += t4.y; s4.z += t4.z; s4.w += t4.w;
+                }
+                v[0] = s4.x; v[1] = s4.y; v[2] = s4.z; v[3] = s4.w;
+            } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+                for (int i2 = 0; i2 < 8; ++i2)
+                    if (i2 == i) { v[0] = out[i2][0]; v[1] = out[i2][1]; v[2] = out[i2][2]; v[3] = out[i2][3]; }
+            }
             const int r = 8 * it + i;
             if (KIND == 0) {
-                if (r < NROWS) { for (int j = 0; j < 4; ++j) dst[r * HP + 4 * jt + j] += out[i][j]; }
-                else if (BIAS && r == NROWS) { for (int j = 0; j < 4; ++j) dstb[4 * jt + j] += out[i][j]; }
+                if (r < NROWS) { for (int j = 0; j < 4; ++j) dst[r * HP + 4 * jt + j] += v[j]; }
+                else if (BIAS && r == NROWS) { for (int j = 0; j < 4; ++j) dstb[4 * jt + j] += v[j]; }
             } else if (KIND == 1) {
-                if (r < NROWS) dst[r] += out[i][0];
-                else if (BIAS && r == NROWS) dstb[0] += out[i][0];
+                if (r < NROWS) dst[r] += v[0];
+                else if (BIAS && r == NROWS) dstb[0] += v[0];
             } else {
-                if (r < DIM) { for (int j = 0; j < 4; ++j) dst[r * HP + 4 * jt + j] += out[i][j]; }
-                else if (r == 2) { for (int j = 0; j < 4; ++j) dstb[4 * jt + j] += out[i][j]; }
+                if (r < DIM) { for (int j = 0; j < 4; ++j) dst[r * HP + 4 * jt + j] += v[j]; }
+                else if (r == 2) { for (int j = 0; j < 4; ++j) dstb[4 * jt + j] += v[j]; }
             }
         }
     }
