@@ -29,6 +29,7 @@ SIGNATURES = {
     "hpv_set_form": (c_int, [c_void_p, c_int, c_int, c_double]),
     "hpv_set_elements": (c_int, [c_void_p, c_int, P_double, P_double, P_int, c_int, c_int, P_double]),
     "hpv_update_rhs_f32": (c_int, [c_void_p, c_void_p]),
+    "hpv_project_field": (c_int, [c_void_p, P_double, c_int, c_int, c_double, c_int, c_int, P_double]),
     "hpv_varloss_forward": (c_int, [c_void_p, P_double, c_void_p, P_double]),
     "hpv_forward_async": (c_int, [c_void_p]),
     "hpv_varloss_backward": (c_int, [c_void_p, P_double, c_int, P_double]),

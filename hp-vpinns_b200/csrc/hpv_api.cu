@@ -642,6 +642,39 @@ int hpv_varloss_forward(hpv_ctx* c, double* lossv, float* residual, double* el_l
     return HPV_OK;
 }
 
+int hpv_project_field(hpv_ctx* c, const double* field, int ltab, int rtab, double sc, int px, int py, double* out) {
+    if (!c || !field || !out) return fail(c, HPV_ERR_ARG, "NULL argument");
+    if (ltab < 0 || ltab >= HPV_NTAB || rtab < 0 || rtab >= HPV_NTAB) return fail(c, HPV_ERR_ARG, "table index out of range");
+    HPV_CK(cudaSetDevice(c->device));
+    { int r = ensure_ready(c); if (r) return r; }
+    const int rows = (c->net.dim == 2) ? c->Q : 1;
+    const size_t npts = (size_t)c->n_el * rows * c->Q, nres = (size_t)c->n_el * c->nty * c->ntx;
+    std::vector<float> hf(npts);
+    for (size_t i = 0; i < npts; ++i) hf[i] = (float)field[i];
+    DevBuf<float> dfield;
+    HPV_CK(dfield.alloc(npts));
+    HPV_CK(cudaMemcpyAsync(dfield.p, hf.data(), npts * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    HpvVarArgs a; fill_var_args(c, a);
+    a.n_terms = 1;
+    a.terms[0] = hpv_term_zero();
+    a.terms[0].ltab = ltab; a.terms[0].rtab = rtab; a.terms[0].s = (float)sc; a.terms[0].px = px; a.terms[0].py = py;
+    a.F = nullptr; a.field_in = dfield.p;
+    const HpvKernelKey k = key_of(c, 0, 0);
+    const HpvFwdSmem fs = hpv_fwd_smem(a, hpv_slot_floats(k.dim, k.mx, k.my, k.hp, HPV_THREADS));
+    HpvLaunch l; memset(&l, 0, sizeof(l));
+    l.kind = HPV_K_VARFWD; l.op = 0; l.grid = c->part.n_ctas; l.block = HPV_THREADS; l.smem = (size_t)fs.total * 4;
+    l.stream = c->stream; l.var = &a;
+    cudaError_t e = hpv_dispatch(k, l);
+    c->launches += 1;
+    std::vector<float> hr(nres);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hr.data(), c->Res.p, nres * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    dfield.release();
+    if (e != cudaSuccess) return fail(c, HPV_ERR_CUDA, std::string("hpv_project_field: ") + cudaGetErrorString(e));
+    for (size_t i = 0; i < nres; ++i) out[i] = hr[i];
+    return HPV_OK;
+}
+
 int hpv_forward_async(hpv_ctx* c) {
     if (!c) return HPV_ERR_ARG;
     HPV_CK(cudaSetDevice(c->device));

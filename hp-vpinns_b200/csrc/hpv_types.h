@@ -44,6 +44,7 @@ struct HpvVarArgs {
     const int* el_ntest;       // [n_el][2] ntx, nty of this element
     int ntx, nty;              // layout sizes of F / Res (max over elements)
     const float* F;            // [n_el][nty][ntx] or null (AdvDiff: Res = U)
+    const float* field_in;     // [n_terms][n_el][rows*Q] or null: point fields given instead of the MLP (RHS assembly)
     // terms
     int n_terms;
     HpvTerm terms[HPV_MAX_TERMS];

@@ -119,13 +119,19 @@ HPV_HD void hpv_varfwd_body(const HpvCta& c, const HpvVarArgs& a) {
                 const int j = p / Q, i = p - j * Q;
                 const float x = fmaf(hwx, s_xi1[i], lox);
                 const float y = (DIM == 2) ? fmaf(hwy, s_xi1[j], loy) : 0.0f;
-                float f[HPV_NFIELDS];
-                hpv_net_point_slot<DIM, MX, MY, HP, ACT>(th, a.nhid, a.off_wo, x, y, s_slot, T, tid, f);
-                for (int t = 0; t < a.n_terms; ++t) {
-                    float g = 0.0f;
+                if (a.field_in) {
+                    // projection of a given field (F_ext assembly, P2D:384-414): no network evaluation
+                    for (int t = 0; t < a.n_terms; ++t)
+                        s_G[t * L.GS + (p - base)] = a.field_in[((size_t)t * a.n_el + e) * npts_el + p];
+                } else {
+                    float f[HPV_NFIELDS];
+                    hpv_net_point_slot<DIM, MX, MY, HP, ACT>(th, a.nhid, a.off_wo, x, y, s_slot, T, tid, f);
+                    for (int t = 0; t < a.n_terms; ++t) {
+                        float g = 0.0f;
 #pragma unroll
-                    for (int k = 0; k < HPV_NFIELDS; ++k) g = fmaf(coef[t][k], f[k], g);
-                    s_G[t * L.GS + (p - base)] = g;
+                        for (int k = 0; k < HPV_NFIELDS; ++k) g = fmaf(coef[t][k], f[k], g);
+                        s_G[t * L.GS + (p - base)] = g;
+                    }
                 }
             }
         }

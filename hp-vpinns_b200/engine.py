@@ -100,6 +100,27 @@ class Engine:
         """host_ptr: address of a (pinned) fp32 host buffer [n_el][nty][ntx]."""
         self._ck(self._lib.hpv_update_rhs_f32(self._h, ctypes.c_void_p(host_ptr)))
 
+    # -- right-hand-side assembly (set-up side; SURVEY 8f) -------------------------------------------------
+    def project_field(self, field, ltab=0, rtab=0, scale=1.0, px=1, py=1):
+        """Projection of a field given at the quadrature points of every element (see hpv_project_field)."""
+        rows = self.Q if self.dim == 2 else 1
+        field = L.f64(field).reshape(self.n_el, rows * self.Q)
+        out = np.zeros((self.n_el, self.nty, self.ntx))
+        self._ck(self._lib.hpv_project_field(self._h, L.dptr(field), int(ltab), int(rtab), float(scale), int(px), int(py), L.dptr(out)))
+        return out
+
+    def assemble_rhs(self, f_ext, lo, hi, xi):
+        """F_ext_total of the reference drivers on the GPU: F[e][k][r] = J sum wx phi_r wy phi_k f(x_p, y_p)
+        (P2D:384-414) / F[e][i] = J sum w f(x_p) phi_i (P1D:275-294).  f_ext is the driver's vectorised function."""
+        lo = L.f64(lo).reshape(-1, self.dim); hi = L.f64(hi).reshape(-1, self.dim); xi = L.f64(xi).ravel()
+        if self.dim == 2:
+            x = lo[:, 0, None] + (hi[:, 0, None] - lo[:, 0, None]) / 2 * (xi[None, :] + 1)         # [n_el][Q]
+            y = lo[:, 1, None] + (hi[:, 1, None] - lo[:, 1, None]) / 2 * (xi[None, :] + 1)
+            field = f_ext(x[:, None, :], y[:, :, None])                                             # [n_el][j][i]
+            return self.project_field(field, 0, 0, 1.0, 1, 1)
+        x = lo[:, 0, None] + (hi[:, 0, None] - lo[:, 0, None]) / 2 * (xi[None, :] + 1)
+        return self.project_field(f_ext(x), 3, 0, 1.0, 1, 0)
+
     # -- the hot path -------------------------------------------------------------------------------------
     def varloss_forward(self, want_residual=True, want_el_loss=False):
         loss = ctypes.c_double(0)

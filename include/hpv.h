@@ -69,6 +69,14 @@ int hpv_set_elements(hpv_ctx* ctx, int n_el, const double* lo, const double* hi,
  * the copy asynchronous). */
 int hpv_update_rhs_f32(hpv_ctx* ctx, const float* F_ext);
 
+/* Projection of a GIVEN point field onto the test functions with the same fused kernel (no network):
+ *   out[e][k][r] = s * Jx^px * Jy^py * sum_p  L[k](eta_p) w_p  field[e][p]  R[r](xi_p) w_p ,
+ * ltab/rtab in {0: Test_fcn, 1: first derivative, 2: second derivative, 3: constant 1 (the 1-D "y" direction)}.
+ * With field = f_ext at the element's quadrature points, ltab = rtab = 0, s = 1, px = py = 1 this is the
+ * right-hand-side assembly F_ext_total of the reference drivers (P2D:384-414; P1D:275-294 with ltab = 3, py = 0).
+ * field [n_el][rows*Q] (rows = Q in 2-D, 1 in 1-D, point p = j*Q + i), out [n_el][nty][ntx]. */
+int hpv_project_field(hpv_ctx* ctx, const double* field, int ltab, int rtab, double s, int px, int py, double* out);
+
 /* lossv and the element residuals (the loop P2D:68-120 / P1D:64-96 / ADI:108-182 as one fused kernel).
  * residual [n_el][nty][ntx] fp32 and el_loss [n_el] may be NULL. */
 int hpv_varloss_forward(hpv_ctx* ctx, double* lossv, float* residual, double* el_loss);

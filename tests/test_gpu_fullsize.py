@@ -95,3 +95,41 @@ def test_limits_are_reported_not_silently_wrong():
     with pytest.raises(hpv_b200.HpvError):
         eng.set_elements(np.zeros((0, 2)), np.zeros((0, 2)), 5, 5)    # empty element batch
     eng.close()
+
+
+def test_rhs_assembly_on_gpu_matches_reference_driver():
+    """F_ext_total assembled by the fused projection kernel (hpv_project_field) against the array the reference
+    driver itself builds (fixture driver_p2d.npz / driver_p1d_3el.npz, produced by the unmodified P2D:384-414 and
+    P1D:275-294 loops) and against the float64 oracle at the C3 size."""
+    import os
+    from tests import _cases as C
+    d = dict(np.load(os.path.join(C.GOLDEN, "driver_p2d.npz")))
+    X, W = O.GaussLobattoJacobiWeights(10, 0, 0)
+    gx, gy = d["grid_x"], d["grid_y"]
+    lo = np.array([[gx[i], gy[j]] for i in range(4) for j in range(4)])
+    hi = np.array([[gx[i + 1], gy[j + 1]] for i in range(4) for j in range(4)])
+    D1, D2 = O.dTest_fcn(5, X)
+    inp = dict(problem="poisson2d", var_form=1, layers=[2, 5, 5, 5, 1], act="tanh", theta=np.zeros(81), xi=X, w=W,
+               T=O.Test_fcn(5, X), D1=D1, D2=D2, d1b=None, lo=lo, hi=hi, ntx=5, nty=5, F=None)
+    eng = G.make_engine(inp)
+    F = eng.assemble_rhs(O.f_ext_2d, lo, hi, X)
+    ref = d["F_ext_total"].reshape(16, 5, 5)
+    assert np.abs(F - ref).max() <= 2e-6 * np.abs(ref).max()
+    eng.close()
+    # 1-D, non-uniform 3-element grid of the reference driver
+    d1 = dict(np.load(os.path.join(C.GOLDEN, "driver_p1d_3el.npz")))
+    xq, wq, g = d1["x_quad"].ravel(), d1["w_quad"].ravel(), d1["grid"]
+    Dq1, Dq2 = O.dTest_fcn(60, xq)
+    inp1 = dict(problem="poisson1d", var_form=1, layers=[1, 5, 1], act="sin", theta=np.zeros(16), xi=xq, w=wq, T=O.Test_fcn(60, xq),
+                D1=Dq1, D2=Dq2, d1b=O.dTest_fcn(60, np.array([-1.0, 1.0]))[0], lo=g[:-1, None], hi=g[1:, None], ntx=60, nty=1, F=None)
+    e1 = G.make_engine(inp1)
+    F1 = e1.assemble_rhs(O.f_ext_1d, g[:-1, None], g[1:, None], xq)
+    ref1 = d1["F_ext_total"].reshape(3, 1, 60)
+    assert np.abs(F1 - ref1).max() <= 1e-5 * np.abs(ref1).max()
+    e1.close()
+    # C3 size against the factorised float64 assembly
+    inp3, (Ws, bs, X3, W3, F3, g3) = _c3()
+    e3 = G.make_engine(inp3)
+    Fg = e3.assemble_rhs(O.f_ext_2d, inp3["lo"], inp3["hi"], X3)
+    assert np.abs(Fg - inp3["F"]).max() <= 2e-6 * np.abs(inp3["F"]).max()
+    e3.close()
