@@ -59,3 +59,99 @@ def test_net_u_and_derivatives(name):
         assert np.allclose(d1[:, 0], c["d1"][:, 0], rtol=1e-4, atol=1e-5)
         assert np.abs(d2[:, 0] - c["d2"][:, 0]).max() <= 1e-5 * max(1.0, np.abs(c["d2"]).max())
     eng.close()
+
+
+def _random_case(problem, layers, act, var_form, Q, N, seed, grid=(np.array([-1.0, -0.3, 1.0]), np.array([-1.0, 0.4, 1.0]))):
+    from oracle import hpvpinn_oracle as O
+    rng = np.random.default_rng(seed)
+    X, W = O.GaussLobattoJacobiWeights(Q, 0, 0)
+    Ws, bs = O.xavier_params(list(layers), seed)
+    bs = [0.1 * rng.standard_normal(b.shape) for b in bs]
+    D1, D2 = O.dTest_fcn(N, X)
+    inp = dict(problem=problem, var_form=var_form, layers=list(layers), act=act, theta=O.pack_theta(Ws, bs), xi=X, w=W,
+               T=O.Test_fcn(N, X), D1=D1, D2=D2, d1b=O.dTest_fcn(N, np.array([-1.0, 1.0]))[0])
+    if problem == "poisson1d":
+        g = np.array([-1.0, -0.2, 0.5, 1.0])
+        F = O.rhs_1d(g, 3 * [N], X, W)
+        inp.update(lo=g[:-1, None], hi=g[1:, None], ntx=N, nty=1, F=np.asarray(F).reshape(3, 1, N))
+        fn = lambda Wt, bt: O.varloss_1d_factorised(Wt, bt, X, W, F, g, var_form)
+    else:
+        gx, gy = grid
+        F = O.rhs_2d_factorised(gx, gy, N, N, X, W)
+        lo = np.array([[gx[i], gy[j]] for i in range(len(gx) - 1) for j in range(len(gy) - 1)])
+        hi = np.array([[gx[i + 1], gy[j + 1]] for i in range(len(gx) - 1) for j in range(len(gy) - 1)])
+        inp.update(lo=lo, hi=hi, ntx=N, nty=N, F=F.reshape(-1, N, N))
+        fn = lambda Wt, bt: O.varloss_2d_factorised(Wt, bt, X, W, F, gx, gy, N, N, var_form)
+    l_ref, g_ref = O.loss_and_grad(lambda Wt, bt: fn(Wt, bt)[0], Ws, bs)
+    r_ref = fn(Ws, bs)[1].detach().numpy()
+    return inp, l_ref, g_ref, r_ref
+
+
+@pytest.mark.parametrize("problem,layers,act,vf,Q,N", [
+    ("poisson2d", [2, 32, 32, 1], "tanh", 1, 14, 7),            # padded width 32
+    ("poisson2d", [2, 27, 31, 29, 1], "tanh", 0, 12, 6),        # unequal widths, padded to 32, second derivatives
+    ("poisson2d", [2, 12, 12, 1], "tanh", 2, 16, 9),            # width padded to 20, var_form 2
+    ("poisson1d", [1, 24, 24, 24, 1], "sin", 1, 40, 20),        # padded width 32, 1-D
+    ("poisson1d", [1, 3, 1], "sin", 2, 9, 4),                   # one hidden layer, width padded to 8
+    ("poisson2d", [2, 6, 6, 6, 6, 6, 6, 6, 6, 1], "tanh", 1, 10, 5),   # eight hidden layers
+])
+def test_other_network_shapes(problem, layers, act, vf, Q, N):
+    inp, l_ref, g_ref, r_ref = _random_case(problem, layers, act, vf, Q, N, seed=Q + N)
+    eng = G.make_engine(inp)
+    loss, res = eng.varloss_forward()
+    g, _ = eng.varloss_backward()
+    assert loss == pytest.approx(l_ref, rel=LOSS_RTOL)
+    assert np.abs(res - r_ref.reshape(res.shape)).max() <= RES_RTOL * np.abs(r_ref).max()
+    tol = 5e-4 if (problem == "poisson1d" and vf == 2) else GRAD_RTOL
+    assert np.abs(g - g_ref).max() <= tol * np.abs(g_ref).max()
+    eng.close()
+
+
+def test_ragged_test_function_counts_on_gpu():
+    c = C.load("p2d_vf1")
+    inp = C.engine_inputs(c)
+    n_el, ntx, nty = inp["lo"].shape[0], inp["ntx"], inp["nty"]
+    ntest = np.array([[ntx - (e % 2), nty - (e % 3 == 0)] for e in range(n_el)], dtype=np.int32)
+    eng = G.make_engine(dict(inp, ntest=ntest))
+    loss, res = eng.varloss_forward()
+    full = C.oracle_lossv(c)[1].reshape(n_el, nty, ntx)
+    want = sum(np.mean(full[e, :ntest[e, 1], :ntest[e, 0]] ** 2) for e in range(n_el))
+    assert loss == pytest.approx(want, rel=LOSS_RTOL)
+    eng.close()
+
+
+def test_many_contexts_alternating_on_one_device():
+    """Contexts share the constant-memory copy of the parameters per kernel translation unit; the library re-stages
+    it when they alternate."""
+    cases = [C.load(n) for n in ("p2d_vf1", "p2d_vf0", "adi_vf0", "p2d_vf2")]      # all padded width 8 -> same copies
+    engs = [G.make_engine(C.engine_inputs(c)) for c in cases]
+    for _ in range(3):
+        for c, e in zip(cases, engs):
+            assert e.varloss_forward(want_residual=False) == pytest.approx(float(c["lossv"]), rel=LOSS_RTOL)
+        for c, e in zip(reversed(cases), reversed(engs)):
+            e.forward_async()
+            g, _ = e.varloss_backward()
+            assert np.abs(g - c["grad_lossv"]).max() <= GRAD_RTOL * np.abs(c["grad_lossv"]).max()
+    for e in engs:
+        e.close()
+
+
+def test_sin_network_in_two_dimensions_and_tanh_in_one():
+    """The oracle's loss restatements fix the activation per problem as the reference does (sin in 1-D, tanh in 2-D);
+    the engine takes it as a parameter, so the other combinations are checked on net_u and its derivatives."""
+    import hpv_b200
+    from oracle import hpvpinn_oracle as O
+    rng = np.random.default_rng(3)
+    for layers, act in (([2, 12, 12, 1], "sin"), ([1, 9, 9, 9, 1], "tanh")):
+        Ws, bs = O.xavier_params(layers, 5)
+        bs = [0.2 * rng.standard_normal(b.shape) for b in bs]
+        pts = 2 * rng.random((333, layers[0])) - 1
+        eng = hpv_b200.Engine(0)
+        eng.set_network(layers, act)
+        eng.set_params(O.pack_theta(Ws, bs))
+        u, d1, d2 = eng.net_u(pts, d1=True, d2=True)
+        uo, d1o, d2o = O.mlp_forward_mode(pts, Ws, bs, act)
+        assert np.allclose(u, uo.numpy(), rtol=1e-5, atol=2e-6)
+        assert np.allclose(d1, d1o.numpy(), rtol=1e-4, atol=1e-5)
+        assert np.abs(d2 - d2o.numpy()).max() <= 1e-5 * max(1.0, np.abs(d2o.numpy()).max())
+        eng.close()
