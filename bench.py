@@ -156,6 +156,9 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------------------------
 FLOP_FWD_PT = 5000.0          # value pass 1720 + two tangent passes 1640
 FLOP_BWD_PT = 10040.0         # reverse sweep: 2 x (adjoint propagation + weight-gradient products), no recompute
+FLOP_BWD_PT_DIR = 6760.0      # the same sweep in the directional mode (value + ONE tangent instead of two): what the
+                              # kernel's algorithm needs, so that roofline.frac is a pipe utilisation and does not
+                              # take credit for the arithmetic the directional form removed
 FLOP_PROJ_EL = 2.688e6        # factorised projection, 2 terms
 
 
@@ -390,7 +393,7 @@ def run_ours(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        flops_bwd = npts_local * FLOP_BWD_PT
+        flops_bwd = npts_local * (FLOP_BWD_PT_DIR if info.get("bwd_directional") else FLOP_BWD_PT)
         ach = flops_bwd / (kern["mlpbwd"] * 1e-6) / 1e12
         traffic = None
         try:
@@ -402,6 +405,7 @@ def run_ours(args):
                     "peak_source": "FP32 FFMA probe kernel measured in this run (hpv_probe_fp32_peak); MEASURED_PEAKS.json "
                                    "carries only HBM GB/s and bf16 tensor TFLOP/s, neither bounds an fp32 FFMA kernel",
                     "algorithmic_flops_per_launch": flops_bwd, "launch_us": kern["mlpbwd"], "traffic": traffic,
+                    "reverse_sweep": "directional (1 tangent)" if info.get("bwd_directional") else "two tangents",
                     "frac_of_measured_bf16_tensor_peak": (ach / peaks["bf16_tflops"]) if "bf16_tflops" in peaks else None,
                     "kernels": {
                         "varfwd": {"us": kern["varfwd"], "algorithmic_gflop": (npts_local * FLOP_FWD_PT + wl["n_el_local"] * FLOP_PROJ_EL) / 1e9},

@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhpv.so")
+# HPV_LIB selects another build of the same library (tuning experiments: build.py --lib PATH)
+LIB_PATH = os.environ.get("HPV_LIB") or os.path.join(HERE, "libhpv.so")
 
 c_int, c_double, c_void_p, c_float = ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_float
 P_int, P_double, P_float = ctypes.POINTER(c_int), ctypes.POINTER(c_double), ctypes.POINTER(c_float)

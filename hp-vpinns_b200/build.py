@@ -24,6 +24,10 @@ NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
 
+# extra nvcc flags for tuning experiments (e.g. HPV_NVCC_EXTRA="-DHPV_BWD_DIR_MIN_CTAS=2"); part of the object digest
+NVCC_FLAGS += os.environ.get("HPV_NVCC_EXTRA", "").split()
+
+
 def _nvcc():
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -94,6 +98,10 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--jobs", type=int, default=None)
+    ap.add_argument("--lib", default=None, help="output path of the shared library (default: next to this file)")
     a = ap.parse_args()
+    if a.lib:
+        LIB = os.path.abspath(a.lib)
+        BUILD = BUILD + "_" + hashlib.sha256(LIB.encode()).hexdigest()[:8]
     build(force=a.force, jobs=a.jobs)
     sys.exit(0)

@@ -70,6 +70,7 @@ struct hpv_ctx {
     DevBuf<float> grad_part, redbuf;
     int bwd_block = 0, bwd_grid = 0, bwd_ctas_per_sm = 0, grad_stride = 0, loss_off = 0;
     size_t bwd_smem = 0, fwd_smem = 0, adj_smem = 0;
+    bool bwd_dir = true;               // allow the directional reverse sweep (HPV_BWD_DIR=0 disables)
     int fwd_ctas_per_sm = 0, adj_grid = 0, slabs_per_el = 0;
     PointSet ps[HPV_MAX_POINT_SETS];
     // training configuration
@@ -110,8 +111,16 @@ int upload(hpv_ctx* c, DevBuf<T>& b, const std::vector<T>& h) {
 
 HpvKernelKey key_of(const hpv_ctx* c, int mx, int my) {
     HpvKernelKey k;
-    k.dim = c->net.dim; k.mx = mx; k.my = my; k.hp = c->net.hp; k.act = c->net.act;
+    k.dim = c->net.dim; k.mx = mx; k.my = my; k.hp = c->net.hp; k.act = c->net.act; k.dir = 0;
     hpv_canon_mode(k.dim, k.mx, k.my);
+    return k;
+}
+
+// Key of the reverse sweep of the variational loss: the directional mode when the form allows it
+// (hpv_form_directional); HPV_BWD_DIR=0 in the environment keeps the two-tangent sweep (A/B measurements).
+HpvKernelKey bwd_key_of(const hpv_ctx* c) {
+    HpvKernelKey k = key_of(c, c->form.mx, c->form.my);
+    k.dir = (c->bwd_dir && hpv_form_directional(c->net.dim, c->form)) ? 1 : 0;
     return k;
 }
 
@@ -166,8 +175,7 @@ void fill_var_args(hpv_ctx* c, HpvVarArgs& a) {
 
 // Choose the block size of the MLP reverse sweep: the largest number of resident threads per SM that the
 // shared-memory plan (HpvBwdSmem) allows.
-int plan_bwd(hpv_ctx* c, int mx, int my, int& block, int& ctas_per_sm, size_t& smem) {
-    const HpvKernelKey k = key_of(c, mx, my);
+int plan_bwd(hpv_ctx* c, const HpvKernelKey& k, int& block, int& ctas_per_sm, size_t& smem) {
     HpvVarArgs va; memset(&va, 0, sizeof(va));
     va.theta_pad_n = c->net.theta_pad_n; va.nhid = c->net.nhid; va.off_wo = hpv_off_wo(c->net.dim, c->net.hp, c->net.nhid);
     HpvBwdArgs ba; memset(&ba, 0, sizeof(ba)); ba.v = va;
@@ -252,7 +260,7 @@ int ensure_ready(hpv_ctx* c) {
     HPV_CK(c->loss.alloc(1));
 
     // backward launch plan
-    { int r = plan_bwd(c, c->form.mx, c->form.my, c->bwd_block, c->bwd_ctas_per_sm, c->bwd_smem); if (r) return r; }
+    { int r = plan_bwd(c, bwd_key_of(c), c->bwd_block, c->bwd_ctas_per_sm, c->bwd_smem); if (r) return r; }
     c->bwd_grid = c->n_sm * c->bwd_ctas_per_sm;
     const long long npts = (long long)c->n_el * rows * c->Q;
     const long long ntiles = (npts + c->bwd_block - 1) / c->bwd_block;
@@ -301,7 +309,7 @@ int launch_mlpbwd_var(hpv_ctx* c) {
     HpvLaunch l; memset(&l, 0, sizeof(l));
     l.kind = HPV_K_MLPBWD; l.op = 0; l.grid = c->bwd_grid; l.block = c->bwd_block; l.smem = c->bwd_smem;
     l.stream = c->stream; l.bwd = &ba;
-    HPV_CK(hpv_dispatch(key_of(c, c->form.mx, c->form.my), l));
+    HPV_CK(hpv_dispatch(bwd_key_of(c), l));
     c->launches += 1;
     return HPV_OK;
 }
@@ -348,7 +356,7 @@ int launch_points(hpv_ctx* c, int mx, int my, int n, const float* pts, float* u,
 
 int launch_mlpbwd_points(hpv_ctx* c, PointSet& ps, int& grid_out) {
     int block = 0, cps = 0; size_t smem = 0;
-    { int r = plan_bwd(c, ps.mx, ps.my, block, cps, smem); if (r) return r; }
+    { int r = plan_bwd(c, key_of(c, ps.mx, ps.my), block, cps, smem); if (r) return r; }
     { int r = refresh_mirror(c, HPV_K_MLPBWD); if (r) return r; }
     HpvBwdArgs ba; memset(&ba, 0, sizeof(ba));
     HpvVarArgs& a = ba.v;
@@ -433,6 +441,7 @@ int hpv_create(hpv_ctx** out, int device) {
     if (prop.major != 10) return fail(c, HPV_ERR_CUDA, "libhpv is built for sm_100a (B200) only");
     hpv_ctx* ctx = new hpv_ctx();
     ctx->device = device; ctx->n_sm = prop.multiProcessorCount;
+    if (const char* ev = getenv("HPV_BWD_DIR")) ctx->bwd_dir = atoi(ev) != 0;
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete ctx;
@@ -912,10 +921,10 @@ int hpv_kernel_info(hpv_ctx* c, int* info, int n) {
     if (!c || !info) return HPV_ERR_ARG;
     HPV_CK(cudaSetDevice(c->device));
     { int r = ensure_ready(c); if (r) return r; }
-    const int v[12] = {c->n_sm, c->part.n_ctas, HPV_THREADS, (int)c->fwd_smem, c->fwd_ctas_per_sm,
+    const int v[13] = {c->n_sm, c->part.n_ctas, HPV_THREADS, (int)c->fwd_smem, c->fwd_ctas_per_sm,
                        c->bwd_grid, c->bwd_block, (int)c->bwd_smem, c->bwd_ctas_per_sm,
-                       c->adj_grid, (int)c->adj_smem, c->net.hp};
-    for (int i = 0; i < n && i < 12; ++i) info[i] = v[i];
+                       c->adj_grid, (int)c->adj_smem, c->net.hp, bwd_key_of(c).dir};
+    for (int i = 0; i < n && i < 13; ++i) info[i] = v[i];
     return HPV_OK;
 }
 

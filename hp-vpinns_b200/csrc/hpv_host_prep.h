@@ -135,6 +135,17 @@ inline bool hpv_form_setup(HpvForm& fm, int problem, int var_form, double V, std
     return true;
 }
 
+// The reverse sweep may carry ONE tangent along the per-point direction (gx, gy) instead of the x and y tangents
+// (HpvMode<2,1,0>::DIR) when the form projects first derivatives only and no coefficient depends on eps (the
+// eps gradient needs u_x, u_y separately): Poisson-2D var_form 1 (P2D:99-105) -- the headline configuration.
+inline bool hpv_form_directional(int dim, const HpvForm& fm) {
+    if (dim != 2 || fm.mx != 1 || fm.my != 1) return false;
+    for (int t = 0; t < fm.n_terms; ++t)
+        for (int f = 0; f < HPV_NFIELDS; ++f)
+            if (fm.terms[t].a1[f] != 0.0f) return false;
+    return true;
+}
+
 // Transposed, quadrature-weighted tables [Q][HPV_NP]:  tab[q][n] = table[n][q] * w[q].
 // T, D1, D2 are the reference's Test_fcn / dTest_fcn outputs on the 1-D nodes, row-major [N][Q].
 // d1_bound [N][2] = phi'_n(-1), phi'_n(+1) (only for the folded boundary table of P1D var_form 3, which

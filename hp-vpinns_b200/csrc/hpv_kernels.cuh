@@ -14,8 +14,19 @@ __global__ void __launch_bounds__(HPV_THREADS, (HpvMode<DIM, MX, MY>::NCH >= 4 ?
     hpv_varfwd_body<DIM, MX, MY, HP, ACT>(c, a);
 }
 
+// Launch bounds of the reverse sweep.  The directional mode (two channels) fits 3 CTAs of 128 threads per SM
+// (168 registers, 75 KB of shared memory each); the other modes keep the full register file per thread.
+#ifndef HPV_BWD_DIR_MIN_CTAS
+#define HPV_BWD_DIR_MIN_CTAS 3         // build-time tuning knob (HPV_NVCC_EXTRA="-DHPV_BWD_DIR_MIN_CTAS=2")
+#endif
+template <int DIM, int MX, int MY>
+struct HpvBwdBounds {
+    static constexpr int THREADS = HpvMode<DIM, MX, MY>::DIR ? 128 : HPV_THREADS;
+    static constexpr int MIN_CTAS = HpvMode<DIM, MX, MY>::DIR ? HPV_BWD_DIR_MIN_CTAS : 1;
+};
+
 template <int DIM, int MX, int MY, int HP, int ACT>
-__global__ void __launch_bounds__(HPV_THREADS, 1) hpv_mlpbwd_kernel(const __grid_constant__ HpvBwdArgs a) {
+__global__ void __launch_bounds__((HpvBwdBounds<DIM, MX, MY>::THREADS), (HpvBwdBounds<DIM, MX, MY>::MIN_CTAS)) hpv_mlpbwd_kernel(const __grid_constant__ HpvBwdArgs a) {
     extern __shared__ __align__(16) unsigned char hpv_smem[];
     HpvCta c;
     c.tid = threadIdx.x; c.nthreads = blockDim.x; c.bid = blockIdx.x; c.nblocks = gridDim.x;
@@ -106,6 +117,9 @@ static cudaError_t hpv_dispatch_hp(const HpvKernelKey& k, const HpvLaunch& l) {
         return hpv_do_act<1, 2, 0, HP, KIND>(k, l);
     }
     if (k.mx == 0 && k.my == 0) return hpv_do_act<2, 0, 0, HP, KIND>(k, l);
+    if constexpr (KIND == HPV_K_MLPBWD) {
+        if (k.dir && k.mx <= 1 && k.my <= 1) return hpv_do_act<2, 1, 0, HP, KIND>(k, l);
+    }
     if (k.mx <= 1 && k.my <= 1) return hpv_do_act<2, 1, 1, HP, KIND>(k, l);
     if (k.mx == 2 && k.my <= 1) return hpv_do_act<2, 2, 1, HP, KIND>(k, l);
     return hpv_do_act<2, 2, 2, HP, KIND>(k, l);

@@ -4,7 +4,8 @@
 #include "hpv_varbwd.cuh"
 #include "hpv_points.cuh"
 
-struct HpvKernelKey { int dim, mx, my, hp, act; };
+// dir != 0 (reverse sweep only): the directional mode HpvMode<2, 1, 0> instead of <2, 1, 1>.
+struct HpvKernelKey { int dim, mx, my, hp, act, dir; };
 
 enum { HPV_K_VARFWD = 0, HPV_K_MLPBWD = 1, HPV_K_POINTS = 2 };
 

@@ -75,6 +75,11 @@ struct HpvMode {
     static constexpr int C_DY = 1 + (DX ? 1 : 0);
     static constexpr int C_EX = C_DY + (DY ? 1 : 0);
     static constexpr int C_EY = C_EX + (EX ? 1 : 0);
+    // <2, 1, 0> is the DIRECTIONAL mode of the reverse sweep (never a forward mode, see hpv_canon_mode): the one
+    // tangent channel carries the derivative along a per-point direction (vx, vy).  For forms that use first
+    // derivatives only, sum_p (gx u_x + gy u_y)(p) = sum_p D_{(gx,gy)(p)} u(p), so the gradient of the loss needs
+    // the value and ONE tangent per point instead of two (2/3 of the arithmetic of mode <2, 1, 1>).
+    static constexpr bool DIR = (DIM == 2) && (MX == 1) && (MY == 0);
 };
 
 // A channel of one layer at one point: HP units held as HP/2 packed pairs (units 2m, 2m+1).
@@ -112,6 +117,21 @@ HPV_HD void hpv_layer1_pre(const float* th, float x, float y, HpvState<DIM, MX, 
         if constexpr (M::DX) z.dx.p[m] = wx;
         if constexpr (M::EX) z.ex.p[m] = hpv_dup(0.0f);
         if constexpr (M::EY) z.ey.p[m] = hpv_dup(0.0f);
+    }
+}
+
+// First layer of the directional mode: z as above, tangent seed dz = vx W1[0,:] + vy W1[1,:].
+template <int HP>
+HPV_HD void hpv_layer1_pre_dir(const float* th, float x, float y, float vx, float vy, HpvState<2, 1, 0, HP>& z) {
+    const float* W1 = th + hpv_off_w1();
+    const float* b1 = th + hpv_off_b1(2, HP);
+    const hpv_pair xx = hpv_dup(x), yy = hpv_dup(y), vxx = hpv_dup(vx), vyy = hpv_dup(vy);
+#pragma unroll
+    for (int m = 0; m < HP / 2; ++m) {
+        const hpv_pair wx = hpv_pack(W1[2 * m], W1[2 * m + 1]);
+        const hpv_pair wy = hpv_pack(W1[HP + 2 * m], W1[HP + 2 * m + 1]);
+        z.v.p[m] = hpv_fma2r(yy, wy, hpv_fma2r(xx, wx, hpv_pack(b1[2 * m], b1[2 * m + 1])));
+        z.dx.p[m] = hpv_fma2r(vyy, wy, hpv_mul2(vxx, wx));
     }
 }
 

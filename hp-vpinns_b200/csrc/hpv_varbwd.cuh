@@ -325,10 +325,26 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
             }
             for (int t = 0; t < a.n_terms; ++t) gbar[t] = ba.Gbar[(size_t)t * ba.n_points + gp];
         }
+        // adjoints of the point fields (u, u_x, u_y, u_xx, u_yy)
+        float gf[HPV_NFIELDS];
+#pragma unroll
+        for (int k = 0; k < HPV_NFIELDS; ++k) gf[k] = 0.0f;
+        for (int t = 0; t < a.n_terms; ++t)
+#pragma unroll
+            for (int k = 0; k < HPV_NFIELDS; ++k) gf[k] = fmaf(gbar[t], coef[t][k], gf[k]);
+        // directional mode: gx u_x + gy u_y = derivative of u along v = (gx, gy).  The tangent channel is seeded
+        // with v, so it carries the scale and its output adjoint is 1.
+        const float vx = gf[1], vy = gf[2];
+        if constexpr (M::DIR) { gf[1] = 1.0f; gf[2] = 0.0f; }
+#define HPV_LAYER1(st)                                                                       \
+        do {                                                                                 \
+            if constexpr (M::DIR) hpv_layer1_pre_dir<HP>(s_th, x, y, vx, vy, st);            \
+            else hpv_layer1_pre<DIM, MX, MY, HP>(s_th, x, y, st);                            \
+        } while (0)
 
         // ---- forward recompute; the pre-activations of hidden layers 1..top-1 stay in their slots ----
         State pre, g;
-        hpv_layer1_pre<DIM, MX, MY, HP>(s_th, x, y, pre);
+        HPV_LAYER1(pre);
         int woff = hpv_off_wl(DIM, HP, 1);                           // constant-memory offsets: own induction variables
 #pragma unroll 1
         for (int l = 1; l <= top; ++l, woff += 2 * HP * HP + HP) {
@@ -343,18 +359,17 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
             hpv_activate<DIM, MX, MY, HP, ACT>(h);
             hpv_store_state<DIM, MX, MY, HP>(X, T, tid, h);
         }
-        float f[HPV_NFIELDS], gf[HPV_NFIELDS];
-        hpv_output_slot<DIM, MX, MY, HP>(Wo, X, T, tid, f);
+        // d loss / d eps needs the fields themselves; the directional mode is only chosen for forms without an
+        // eps-dependent coefficient (hpv_form_directional), where this sum is identically 0
+        if constexpr (!M::DIR) {
+            float f[HPV_NFIELDS];
+            hpv_output_slot<DIM, MX, MY, HP>(Wo, X, T, tid, f);
+            for (int t = 0; t < a.n_terms; ++t) {
+                float d1 = 0.0f;
 #pragma unroll
-        for (int k = 0; k < HPV_NFIELDS; ++k) gf[k] = 0.0f;
-        for (int t = 0; t < a.n_terms; ++t) {
-            float d1 = 0.0f;
-#pragma unroll
-            for (int k = 0; k < HPV_NFIELDS; ++k) {
-                gf[k] = fmaf(gbar[t], coef[t][k], gf[k]);
-                d1 = fmaf(coef1[t][k], f[k], d1);
+                for (int k = 0; k < HPV_NFIELDS; ++k) d1 = fmaf(coef1[t][k], f[k], d1);
+                deps = fmaf(gbar[t], d1, deps);
             }
-            deps = fmaf(gbar[t], d1, deps);
         }
 
         // ---- output layer: Wo/bo gradient (left factor h_top in X), adjoint of h_top ----
@@ -388,7 +403,7 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
             hpv_store_state<DIM, MX, MY, HP>(X, T, tid, g);
             float* INl = (l - 1 >= 1) ? HPV_P(l - 1) : H0;
             if (l - 1 >= 1) hpv_load_state<DIM, MX, MY, HP>(INl, T, tid, pre);
-            else hpv_layer1_pre<DIM, MX, MY, HP>(s_th, x, y, pre);
+            else HPV_LAYER1(pre);
             {
                 State h = pre;
                 hpv_activate<DIM, MX, MY, HP, ACT>(h);                  // h_{l-1}: left factor of the W_l gradient
@@ -408,8 +423,12 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
         {
             HpvF4 o;
             o.x = x; o.y = y; o.z = 1.0f; o.w = 0.0f; hpv_st4(s_in0 + (0 * T + tid) * 4, o);
-            o.x = 1.0f; o.y = 0.0f; o.z = 0.0f; o.w = 0.0f; hpv_st4(s_in0 + (1 * T + tid) * 4, o);
-            o.x = 0.0f; o.y = 1.0f; hpv_st4(s_in0 + (2 * T + tid) * 4, o);
+            if constexpr (M::DIR) {                    // the tangent seed is v . W1: its left factor is v
+                o.x = vx; o.y = vy; o.z = 0.0f; o.w = 0.0f; hpv_st4(s_in0 + (1 * T + tid) * 4, o);
+            } else {
+                o.x = 1.0f; o.y = 0.0f; o.z = 0.0f; o.w = 0.0f; hpv_st4(s_in0 + (1 * T + tid) * 4, o);
+                o.x = 0.0f; o.y = 1.0f; hpv_st4(s_in0 + (2 * T + tid) * 4, o);
+            }
         }
         hpv_sync(c);
         // channels that feed W1: value (x, y, 1), d/dx (1, 0, 0), d/dy (0, 1, 0); second-derivative seeds are 0.
@@ -421,6 +440,7 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
             hpv_wgrad_gemm<4, SP, nch1, 4, HP / 4, false, 2, HP, DIM>(c, s_in0, X, gW1, gb1, s_scr);
             hpv_sync(c);
         }
+#undef HPV_LAYER1
     }
 #undef HPV_P
 

@@ -119,7 +119,9 @@ int hpv_reset_optimizer(hpv_ctx* ctx);
  * and the four point losses BEFORE each update (i.e. at the parameters the gradient was taken at); may be NULL. */
 int hpv_train_steps(hpv_ctx* ctx, int nsteps, double* loss_history);
 
-/* Measurement helpers for bench.py: launch counter of this context, the dominant kernels' launch geometry,
+/* Measurement helpers for bench.py: launch counter of this context, the dominant kernels' launch geometry
+ * (info[0..12] = SMs, forward grid/block/smem/CTAs per SM, reverse-sweep grid/block/smem/CTAs per SM, adjoint
+ * projection grid/smem, padded hidden width, 1 if the reverse sweep runs in the directional mode),
  * and the FP32-FFMA probe (variant 0 register operands, 1 constant-bank operand, 2 packed f32x2); the probe
  * returns the achieved TFLOP/s measured with CUDA events on the context's stream. */
 long long hpv_launch_count(hpv_ctx* ctx);

@@ -39,6 +39,7 @@ void run_grid(int grid, int block, size_t smem_bytes, Body body) {
 }
 
 struct Key { int dim, mx, my, hp, act; };
+int g_bwd_dir = 1;      // as hpv_ctx::bwd_dir: allow the directional reverse sweep where the form permits it
 
 #define EMU_ACT(DIM, MX, MY, HP, CALL)                                             \
     if (k.act == HPV_ACT_TANH) { CALL(DIM, MX, MY, HP, HPV_ACT_TANH); }            \
@@ -70,6 +71,17 @@ int emu_bwd(const Key& k, const HpvBwdArgs& a, int grid, int block) {
         HpvBwdSmem<DIM, MX, MY, HP> L(a.v.theta_pad_n, a.v.nhid, block);                                 \
         run_grid(grid, block, (size_t)L.total * 4, [&](const HpvCta& c) { hpv_mlpbwd_body<DIM, MX, MY, HP, ACT>(c, a); }); \
     }
+    if (k.dim == 2 && k.mx == 1 && k.my == 1 && g_bwd_dir && a.pts == nullptr) {
+        bool dir = true;
+        for (int t = 0; t < a.v.n_terms; ++t)
+            for (int f = 0; f < HPV_NFIELDS; ++f) if (a.v.terms[t].a1[f] != 0.0f) dir = false;
+        if (dir) {
+            if (k.hp == 8) { EMU_ACT(2, 1, 0, 8, CALL) }
+            else if (k.hp == 20) { EMU_ACT(2, 1, 0, 20, CALL) }
+            else return -4;
+            return 0;
+        }
+    }
     EMU_DISPATCH(CALL)
 #undef CALL
     return 0;
@@ -92,6 +104,8 @@ void reduce_grad(const std::vector<float>& part, int n_parts, int stride, int n,
 }  // namespace
 
 extern "C" {
+
+void hpv_emu_set_bwd_dir(int on) { g_bwd_dir = on; }
 
 // Variational loss forward (+ backward when grad_theta != NULL) on emulated CTAs.
 //   n_ctas_fwd / n_ctas_bwd / bwd_block choose the launch geometry (to exercise the split-element paths).

@@ -107,6 +107,33 @@ def test_other_network_shapes(problem, layers, act, vf, Q, N):
     eng.close()
 
 
+@pytest.mark.parametrize("name", ["p2d_vf1", "p2d_vf1_w20", "adi_vf1"])
+def test_directional_and_two_tangent_reverse_sweeps(name, monkeypatch):
+    """The reverse sweep of first-derivative forms without an eps-dependent coefficient (Poisson-2D var_form 1)
+    runs in the directional mode by default; HPV_BWD_DIR=0 (read by hpv_create) keeps the two-tangent sweep.  Both
+    must give the reference gradient.  AdvDiff var_form 1 has an eps-dependent term and never takes the
+    directional kernel: its gradients (incl. d/d eps) must not depend on the switch."""
+    c = C.load(name)
+    inp = C.engine_inputs(c)
+    gref = c["grad_lossv"]
+    got = {}
+    for d in ("0", "1"):
+        monkeypatch.setenv("HPV_BWD_DIR", d)
+        eng = G.make_engine(inp)
+        eng.forward_async()
+        got[d] = eng.varloss_backward()
+        info = eng.kernel_info()
+        eng.close()
+        assert np.abs(got[d][0] - gref).max() <= GRAD_RTOL * np.abs(gref).max()
+        assert info["bwd_directional"] == (1 if (d == "1" and c["kind"] == "poisson2d") else 0)
+    if c["kind"] == "advdiff":
+        assert np.array_equal(got["0"][0], got["1"][0]) and got["0"][1] == got["1"][1]
+        assert got["1"][1] == pytest.approx(float(c["grad_lossv_eps"][0]), rel=1e-4)
+    else:
+        assert not np.array_equal(got["0"][0], got["1"][0])
+        assert np.abs(got["0"][0] - got["1"][0]).max() <= 2e-5 * np.abs(gref).max()
+
+
 def test_ragged_test_function_counts_on_gpu():
     c = C.load("p2d_vf1")
     inp = C.engine_inputs(c)

@@ -29,6 +29,26 @@ def test_emulated_forward_backward(name):
         assert ge == pytest.approx(o[3][0], rel=1e-4)
 
 
+@pytest.mark.parametrize("name", ["p2d_vf1", "p2d_vf1_w20"])
+def test_directional_reverse_sweep_matches_two_tangent_sweep(name):
+    """Poisson-2D var_form 1 projects first derivatives only, so the reverse sweep carries ONE tangent along the
+    per-point direction (gbar_x, gbar_y) (HpvMode<2,1,0>::DIR) instead of the x and y tangents.  Both sweeps give
+    the gradient of the same loss: each against the oracle, and against each other."""
+    c = C.load(name)
+    inp = C.engine_inputs(c)
+    gref = C.oracle_lossv(c)[2]
+    out = {}
+    try:
+        for d in (0, 1):
+            E.lib().hpv_emu_set_bwd_dir(d)
+            out[d] = E.varloss(**inp)[3]
+            assert np.abs(out[d] - gref).max() <= 1e-4 * np.abs(gref).max()
+    finally:
+        E.lib().hpv_emu_set_bwd_dir(1)
+    assert not np.array_equal(out[0], out[1])           # two different kernels ...
+    assert np.abs(out[0] - out[1]).max() <= 2e-5 * np.abs(gref).max()      # ... one gradient
+
+
 def test_partition_independence_and_determinism():
     """Same numbers whatever the number of CTAs an element is split over (fixed-order reductions)."""
     c = C.load("p2d_vf1_w20")          # Q = 12 -> 144 points per element -> one tile per element
