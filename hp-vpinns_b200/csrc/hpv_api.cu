@@ -71,6 +71,7 @@ struct hpv_ctx {
     int bwd_block = 0, bwd_grid = 0, bwd_ctas_per_sm = 0, grad_stride = 0, loss_off = 0;
     size_t bwd_smem = 0, fwd_smem = 0, adj_smem = 0;
     bool bwd_dir = true;               // allow the directional reverse sweep (HPV_BWD_DIR=0 disables)
+    bool adam_direct = true;           // Adam writes the constant-memory mirrors in place (HPV_ADAM_DIRECT=0 disables)
     int fwd_ctas_per_sm = 0, adj_grid = 0, slabs_per_el = 0;
     PointSet ps[HPV_MAX_POINT_SETS];
     // training configuration
@@ -314,11 +315,12 @@ int launch_mlpbwd_var(hpv_ctx* c) {
     return HPV_OK;
 }
 
-int launch_gradreduce(hpv_ctx* c, int n_parts, int accumulate) {
+// `la` non-null: the launch also assembles the loss values (one extra CTA), see hpv_gradreduce_kernel.
+int launch_gradreduce(hpv_ctx* c, int n_parts, int accumulate, const HpvLossArgs* la = nullptr) {
     HpvGradReduceArgs g;
     g.grad_part = c->grad_part.p; g.n_parts = n_parts; g.stride = c->grad_stride; g.n = c->net.theta_pad_n + 1;
     g.grad_pad = c->redbuf.p; g.accumulate = accumulate;
-    HPV_CK(hpv_launch_gradreduce(g, c->stream));
+    HPV_CK(hpv_launch_gradreduce(g, la, c->stream));
     c->launches += 1;
     return HPV_OK;
 }
@@ -379,30 +381,8 @@ int launch_mlpbwd_points(hpv_ctx* c, PointSet& ps, int& grid_out) {
     return HPV_OK;
 }
 
-struct LossArgs {
-    const double* lossv; float wv; int use_v;
-    const float* blk[HPV_MAX_POINT_SETS]; int nblk[HPV_MAX_POINT_SETS];
-    float* out;     // [8]: total, lossv, point losses
-};
-
-__global__ void hpv_losses_kernel(const LossArgs a) {
-    const int lane = threadIdx.x;
-    float total = 0.0f;
-    float lv = a.use_v ? (float)a.lossv[0] : 0.0f;
-    total = a.wv * lv;
-    float pl[HPV_MAX_POINT_SETS];
-    for (int s = 0; s < HPV_MAX_POINT_SETS; ++s) {
-        float acc = 0.0f;
-        if (a.blk[s]) for (int i = lane; i < a.nblk[s]; i += 32) acc += a.blk[s][i];
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        pl[s] = acc;
-        total += acc;
-    }
-    if (lane == 0) {
-        a.out[0] = total; a.out[1] = lv;
-        for (int s = 0; s < HPV_MAX_POINT_SETS; ++s) a.out[2 + s] = pl[s];
-    }
-}
+// total = wv*lossv + point losses, for the case that no gradient reduction ran (nothing to fuse it into)
+__global__ void hpv_losses_kernel(const HpvLossArgs a) { hpv_losses_warp(a, threadIdx.x); }
 
 int need_net(hpv_ctx* c) {
     if (!c) return HPV_ERR_ARG;
@@ -442,6 +422,7 @@ int hpv_create(hpv_ctx** out, int device) {
     hpv_ctx* ctx = new hpv_ctx();
     ctx->device = device; ctx->n_sm = prop.multiProcessorCount;
     if (const char* ev = getenv("HPV_BWD_DIR")) ctx->bwd_dir = atoi(ev) != 0;
+    if (const char* ev = getenv("HPV_ADAM_DIRECT")) ctx->adam_direct = atoi(ev) != 0;
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete ctx;
@@ -697,10 +678,19 @@ static int unpad_grad(hpv_ctx* c, int update) {
     a.theta = c->master.p; a.m = c->adam_m.p; a.v = c->adam_v.p; a.theta_pad = c->theta_pad.p; a.eps = c->eps.p;
     a.grad_out = c->grad_out.p; a.train_eps = c->train_eps;
     a.lr = (float)c->lr; a.b1 = (float)c->b1; a.b2 = (float)c->b2; a.eps_hat = (float)c->eps_hat;
-    a.step = c->step.p; a.step_rw = c->step.p; a.update = update;
+    a.step = c->step.p; a.update = update;
+    bool wrote[3] = {false, false, false};
+    if (update && c->adam_direct) {
+        // mirrors this context owns right now take the update in place; a mirror that was already stale stays stale
+        std::lock_guard<std::mutex> lock(g_owner_mutex);
+        const int hpi = c->net.hp == 8 ? 0 : (c->net.hp == 20 ? 1 : 2);
+        for (int k = 0; k < 3; ++k)
+            if (c->mirror[k] && g_owner[c->device & 15][hpi][k] == c) { a.mirror[k] = c->mirror[k]; wrote[k] = true; }
+    }
     HPV_CK(hpv_launch_adam(a, c->stream));
-    c->launches += update ? 2 : 1;
-    if (update) theta_changed(c);
+    c->launches += 1;
+    if (update)
+        for (int k = 0; k < 3; ++k) if (!wrote[k]) c->mirror_stale[k] = true;
     return HPV_OK;
 }
 
@@ -821,32 +811,38 @@ int hpv_loss_and_grad(hpv_ctx* c) {
     HPV_CK(cudaSetDevice(c->device));
     const bool use_v = c->wv != 0.0;
     if (use_v || !c->redbuf.p) { int r = ensure_ready(c); if (r) return r; }
-    int acc = 0;
+    // The gradient reduction of a loss must run before the next reverse sweep overwrites the per-CTA partials;
+    // the last one of the step also assembles the loss values (saves a launch).
+    int acc = 0, pending = -1;
     if (use_v) {
         int r = launch_forward(c);
         if (!r) r = launch_adjproj(c);
         if (!r) r = launch_mlpbwd_var(c);
-        if (!r) r = launch_gradreduce(c, c->bwd_grid, 0);
         if (r) return r;
-        acc = 1;
+        pending = c->bwd_grid;
     }
-    LossArgs la; memset(&la, 0, sizeof(la));
+    HpvLossArgs la; memset(&la, 0, sizeof(la));
     la.lossv = c->loss.p; la.wv = (float)c->wv; la.use_v = use_v ? 1 : 0; la.out = c->redbuf.p + c->loss_off;
     for (int s = 0; s < HPV_MAX_POINT_SETS; ++s) {
         if (!(c->mask & (1u << s)) || !c->ps[s].active) continue;
         PointSet& ps = c->ps[s];
         int grid = 0;
         int r = launch_points(c, ps.mx, ps.my, ps.n, ps.pts.p, nullptr, nullptr, nullptr, &ps, true);
+        if (!r && pending >= 0) { r = launch_gradreduce(c, pending, acc); acc = 1; pending = -1; }
         if (!r) r = launch_mlpbwd_points(c, ps, grid);
-        if (!r) r = launch_gradreduce(c, grid, acc);
         if (r) return r;
-        acc = 1;
+        pending = grid;
         la.blk[s] = ps.blk_loss.p; la.nblk[s] = ps.n_ctas;
     }
-    if (!acc) HPV_CK(cudaMemsetAsync(c->redbuf.p, 0, c->loss_off * sizeof(float), c->stream));
-    hpv_losses_kernel<<<1, 32, 0, c->stream>>>(la);
-    HPV_CK(cudaGetLastError());
-    c->launches += 1;
+    if (pending >= 0) {
+        int r = launch_gradreduce(c, pending, acc, &la);
+        if (r) return r;
+    } else {
+        HPV_CK(cudaMemsetAsync(c->redbuf.p, 0, c->loss_off * sizeof(float), c->stream));
+        hpv_losses_kernel<<<1, 32, 0, c->stream>>>(la);
+        HPV_CK(cudaGetLastError());
+        c->launches += 1;
+    }
     return HPV_OK;
 }
 

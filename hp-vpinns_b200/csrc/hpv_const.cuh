@@ -8,7 +8,7 @@
 #include "hpv_types.h"
 
 #if defined(__CUDACC__)
-__constant__ float hpv_c_theta[HPV_CTHETA_MAX];
+__constant__ __align__(16) float hpv_c_theta[HPV_CTHETA_MAX];
 #endif
 
 #if defined(__CUDA_ARCH__)

@@ -14,6 +14,8 @@
 struct HpvEmu;                                   // host emulation state (tests/emu/hpv_emu.h)
 #if !HPV_DEVICE_CODE
 void hpv_emu_barrier(HpvEmu* e);                 // provided by the emulation harness only
+void hpv_emu_warp_barrier(HpvEmu* e, int warp);
+float hpv_emu_shfl_xor(HpvEmu* e, int tid, float v, int mask);
 #endif
 
 struct HpvCta {
@@ -27,6 +29,23 @@ HPV_HD void hpv_sync(const HpvCta& c) {
     __syncthreads();
 #else
     hpv_emu_barrier(c.emu);
+#endif
+}
+
+// Warp-level synchronisation and exchange (every lane of the warp must call them).
+HPV_HD void hpv_syncwarp(const HpvCta& c) {
+#if HPV_DEVICE_CODE
+    __syncwarp();
+#else
+    hpv_emu_warp_barrier(c.emu, c.tid >> 5);
+#endif
+}
+
+HPV_HD float hpv_shfl_xor(const HpvCta& c, float v, int mask) {
+#if HPV_DEVICE_CODE
+    return __shfl_xor_sync(0xffffffffu, v, mask);
+#else
+    return hpv_emu_shfl_xor(c.emu, c.tid, v, mask);
 #endif
 }
 

@@ -75,13 +75,16 @@ static cudaError_t hpv_do(const HpvLaunch& l) {
     } else if constexpr (KIND == HPV_K_MLPBWD) {
         auto k = hpv_mlpbwd_kernel<DIM, MX, MY, HP, ACT>;
         if (l.op == 2) {
-            HpvBwdSmem<DIM, MX, MY, HP> L(l.bwd->v.theta_pad_n, l.bwd->v.nhid, l.block);
+            HpvBwdSmem<DIM, MX, MY, HP> L(l.bwd->v.nhid, l.block);
             *l.out = (long long)L.total * 4;
             return cudaSuccess;
         }
         if ((err = hpv_prepare(k, l.smem, prepared)) != cudaSuccess) return err;
         if (l.op == 1) {
             int n = 0;
+            cudaFuncAttributes fa;
+            if ((err = cudaFuncGetAttributes(&fa, k)) != cudaSuccess) return err;
+            if (l.block > fa.maxThreadsPerBlock) { *l.out = 0; return cudaSuccess; }     // beyond the launch bounds
             err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, l.block, l.smem);
             *l.out = n;
             return err;

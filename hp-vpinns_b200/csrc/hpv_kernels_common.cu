@@ -1,6 +1,7 @@
 // Mode-independent kernels: adjoint projection (K1), partial-gradient reduction (K3), the TF1-semantics Adam
 // update (tf.train.AdamOptimizer, P2D:131-132 / P1D:102-104 / ADI:191-193) and the FP32-FFMA peak probe that
 // bench.py uses as the roofline denominator of the FFMA kernels.
+#include <string.h>
 #include "hpv_launch.h"
 
 __global__ void __launch_bounds__(HPV_THREADS, 1) hpv_adjproj_kernel(const __grid_constant__ HpvAdjArgs a) {
@@ -25,56 +26,71 @@ cudaError_t hpv_launch_adjproj(const HpvAdjArgs& a, int grid, size_t smem, cudaS
     return cudaGetLastError();
 }
 
-__global__ void __launch_bounds__(256) hpv_gradreduce_kernel(const HpvGradReduceArgs a) {
+// CTAs 0 .. nred-1 reduce 32 gradient entries each; with has_loss the last CTA assembles the loss values.
+__global__ void __launch_bounds__(256) hpv_gradreduce_kernel(const HpvGradReduceArgs a, const HpvLossArgs la, int nred) {
     __shared__ __align__(16) unsigned char smem[8 * 32 * 4];
+    if ((int)blockIdx.x >= nred) {
+        if (threadIdx.x < 32) hpv_losses_warp(la, threadIdx.x);
+        return;
+    }
     HpvCta c;
-    c.tid = threadIdx.x; c.nthreads = blockDim.x; c.bid = blockIdx.x; c.nblocks = gridDim.x;
+    c.tid = threadIdx.x; c.nthreads = blockDim.x; c.bid = blockIdx.x; c.nblocks = nred;
     c.smem = smem; c.emu = nullptr;
     hpv_gradreduce_body(c, a);
 }
 
-cudaError_t hpv_launch_gradreduce(const HpvGradReduceArgs& a, cudaStream_t s) {
-    int grid = (a.n + 31) / 32;
-    hpv_gradreduce_kernel<<<grid, 256, 0, s>>>(a);
+cudaError_t hpv_launch_gradreduce(const HpvGradReduceArgs& a, const HpvLossArgs* la, cudaStream_t s) {
+    const int nred = (a.n + 31) / 32;
+    HpvLossArgs l0;
+    memset(&l0, 0, sizeof(l0));
+    hpv_gradreduce_kernel<<<nred + (la ? 1 : 0), 256, 0, s>>>(a, la ? *la : l0, nred);
     return cudaGetLastError();
 }
 
-// One thread per parameter (reference order, eps last).  Always un-pads the gradient; with update != 0 applies
+// One CTA; thread-strided over the parameters (reference order, eps last).  Always un-pads the gradient; with
+// update != 0 applies
 //   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  lr_t = lr sqrt(1-b2^t)/(1-b1^t);  theta -= lr_t m/(sqrt(v)+eps_hat)
-// (eps_hat outside the bias correction, as in TF1) in float64 master copies, then refreshes the fp32 padded
-// parameters the kernels read.
-__global__ void hpv_adam_kernel(const HpvAdamArgs a) {
+// (eps_hat outside the bias correction, as in TF1) in float64 master copies, refreshes the fp32 padded
+// parameters the kernels read -- in global memory and in the constant-memory mirrors this context owns (the
+// constant caches are invalidated at the next launch, so the following kernels see the update) -- and advances
+// the step counter (single CTA: every thread has read t before thread 0 stores t + 1).
+__global__ void __launch_bounds__(1024) hpv_adam_kernel(const HpvAdamArgs a) {
     const HpvAdamArgs& d = a;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > a.n_theta) return;
-    const bool is_eps = (i == a.n_theta);
-    const double g = (double)(is_eps ? a.grad_pad[a.theta_pad_n] : a.grad_pad[a.pad_index[i]]);
-    if (d.grad_out) d.grad_out[i] = g;
-    if (!a.update) return;
-    if (is_eps && !a.train_eps) return;
-    const int t = a.step[0] + 1;
+    const int t = a.update ? a.step[0] + 1 : 0;
     const double b1 = a.b1, b2 = a.b2;
-    const double m = b1 * d.m[i] + (1.0 - b1) * g;
-    const double v = b2 * d.v[i] + (1.0 - b2) * g * g;
-    const double lr_t = (double)a.lr * sqrt(1.0 - pow(b2, (double)t)) / (1.0 - pow(b1, (double)t));
-    const double th = d.theta[i] - lr_t * m / (sqrt(v) + (double)a.eps_hat);
-    d.m[i] = m; d.v[i] = v; d.theta[i] = th;
-    if (is_eps) a.eps[0] = (float)th;
-    else {
-        a.theta_pad[a.pad_index[i]] = (float)th;
-        const int i2 = a.pad_index2[i];
-        if (i2 >= 0) a.theta_pad[i2] = (float)th;
+    const double lr_t = a.update ? (double)a.lr * sqrt(1.0 - pow(b2, (double)t)) / (1.0 - pow(b1, (double)t)) : 0.0;
+    __syncthreads();
+    for (int i = threadIdx.x; i <= a.n_theta; i += blockDim.x) {
+        const bool is_eps = (i == a.n_theta);
+        const double g = (double)(is_eps ? a.grad_pad[a.theta_pad_n] : a.grad_pad[a.pad_index[i]]);
+        if (d.grad_out) d.grad_out[i] = g;
+        if (!a.update) continue;
+        if (is_eps && !a.train_eps) continue;
+        const double m = b1 * d.m[i] + (1.0 - b1) * g;
+        const double v = b2 * d.v[i] + (1.0 - b2) * g * g;
+        const double th = d.theta[i] - lr_t * m / (sqrt(v) + (double)a.eps_hat);
+        d.m[i] = m; d.v[i] = v; d.theta[i] = th;
+        if (is_eps) a.eps[0] = (float)th;
+        else {
+            const int i1 = a.pad_index[i], i2 = a.pad_index2[i];
+            const float tf = (float)th;
+            a.theta_pad[i1] = tf;
+            if (i2 >= 0) a.theta_pad[i2] = tf;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                float* mk = a.mirror[k];
+                if (mk) { mk[i1] = tf; if (i2 >= 0) mk[i2] = tf; }
+            }
+        }
     }
+    if (a.update && threadIdx.x == 0) a.step[0] = t;
 }
-
-__global__ void hpv_step_inc_kernel(int* step) { step[0] += 1; }
 
 cudaError_t hpv_launch_adam(const HpvAdamArgs& a, cudaStream_t s) {
     const int n = a.n_theta + 1;
-    hpv_adam_kernel<<<(n + 127) / 128, 128, 0, s>>>(a);
-    cudaError_t err = cudaGetLastError();
-    if (err != cudaSuccess) return err;
-    if (a.update) hpv_step_inc_kernel<<<1, 1, 0, s>>>(a.step_rw);
+    int block = ((n + 31) / 32) * 32;
+    if (block > 1024) block = 1024;
+    hpv_adam_kernel<<<1, block, 0, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -49,7 +49,34 @@ inline cudaError_t hpv_dispatch(const HpvKernelKey& k, const HpvLaunch& l) {
 
 // mode-independent kernels (hpv_kernels_common.cu)
 cudaError_t hpv_launch_adjproj(const HpvAdjArgs& a, int grid, size_t smem, cudaStream_t s);
-cudaError_t hpv_launch_gradreduce(const HpvGradReduceArgs& a, cudaStream_t s);
+// Loss assembly: out[0] = wv*lossv + sum of the point losses, out[1] = lossv, out[2+s] = point loss s
+// (sum of its per-CTA partials).  One warp.
+#define HPV_MAX_POINT_SETS 4
+struct HpvLossArgs {
+    const double* lossv; float wv; int use_v;
+    const float* blk[HPV_MAX_POINT_SETS]; int nblk[HPV_MAX_POINT_SETS];
+    float* out;     // [8]: total, lossv, point losses
+};
+#if defined(__CUDACC__)
+__device__ inline void hpv_losses_warp(const HpvLossArgs& a, int lane) {
+    const float lv = a.use_v ? (float)a.lossv[0] : 0.0f;
+    float total = a.wv * lv;
+    float pl[HPV_MAX_POINT_SETS];
+    for (int s = 0; s < HPV_MAX_POINT_SETS; ++s) {
+        float acc = 0.0f;
+        if (a.blk[s]) for (int i = lane; i < a.nblk[s]; i += 32) acc += a.blk[s][i];
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        pl[s] = acc;
+        total += acc;
+    }
+    if (lane == 0) {
+        a.out[0] = total; a.out[1] = lv;
+        for (int s = 0; s < HPV_MAX_POINT_SETS; ++s) a.out[2 + s] = pl[s];
+    }
+}
+#endif
+// la non-null: one extra CTA assembles the loss values in the same launch
+cudaError_t hpv_launch_gradreduce(const HpvGradReduceArgs& a, const HpvLossArgs* la, cudaStream_t s);
 struct HpvAdamArgs {
     const float* grad_pad;     // padded gradient (+ d eps at index theta_pad_n)
     const int* pad_index;      // [n_theta] reference-order index -> padded index
@@ -58,12 +85,13 @@ struct HpvAdamArgs {
     double* theta;             // [n_theta + 1] float64 master parameters, reference order, eps last
     double* m; double* v;      // Adam moments, same layout
     float* theta_pad;          // padded copy read by the kernels
+    float* mirror[3];          // constant-memory mirrors of theta_pad this context currently owns (or null): the
+                               // update is written into them directly, saving the device-to-device re-staging copies
     float* eps;                // device scalar read by the kernels
     double* grad_out;          // [n_theta + 1] unpadded gradient or null
     int train_eps;
     float lr, b1, b2, eps_hat;
-    const int* step;           // device step counter t >= 1 (incremented by the kernel when update != 0)
-    int* step_rw;
+    int* step;                 // device step counter (the update uses t = step + 1 and stores it back)
     int update;                // 0: only unpad the gradient, 1: also apply the Adam update
 };
 cudaError_t hpv_launch_adam(const HpvAdamArgs& a, cudaStream_t s);

@@ -27,6 +27,8 @@ HPV_HD hpv_pair hpv_mul2(hpv_pair a, hpv_pair b) { hpv_pair r; asm("mul.rn.f32x2
 HPV_HD hpv_pair hpv_add2(hpv_pair a, hpv_pair b) { hpv_pair r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 HPV_HD float hpv_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 HPV_HD float hpv_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// Two consecutive floats at an 8-byte aligned address as one 64-bit load (constant memory: one LDCU.64).
+HPV_HD hpv_pair hpv_ld_pair(const float* p) { return *reinterpret_cast<const unsigned long long*>(p); }
 #else
 struct hpv_pair { float lo, hi; };
 HPV_HD hpv_pair hpv_pack(float lo, float hi) { hpv_pair p; p.lo = lo; p.hi = hi; return p; }
@@ -35,6 +37,7 @@ HPV_HD void hpv_fma2(hpv_pair& c, hpv_pair a, hpv_pair b) { c.lo = fmaf(a.lo, b.
 HPV_HD hpv_pair hpv_fma2r(hpv_pair a, hpv_pair b, hpv_pair c) { hpv_pair r; r.lo = fmaf(a.lo, b.lo, c.lo); r.hi = fmaf(a.hi, b.hi, c.hi); return r; }
 HPV_HD hpv_pair hpv_mul2(hpv_pair a, hpv_pair b) { hpv_pair r; r.lo = a.lo * b.lo; r.hi = a.hi * b.hi; return r; }
 HPV_HD hpv_pair hpv_add2(hpv_pair a, hpv_pair b) { hpv_pair r; r.lo = a.lo + b.lo; r.hi = a.hi + b.hi; return r; }
+HPV_HD hpv_pair hpv_ld_pair(const float* p) { hpv_pair r; r.lo = p[0]; r.hi = p[1]; return r; }
 HPV_HD float hpv_ex2(float x) { return exp2f(x); }
 HPV_HD float hpv_rcp(float x) { return 1.0f / x; }
 #endif

@@ -79,7 +79,7 @@ HPV_HD void hpv_matmul_slot(const float* W, const float* b, const float* slot, i
     hpv_pair acc[NCH][HP / 2];
 #pragma unroll
     for (int m = 0; m < HP / 2; ++m) {
-        acc[0][m] = BIAS ? hpv_pack(b[2 * m], b[2 * m + 1]) : hpv_dup(0.0f);
+        acc[0][m] = BIAS ? hpv_ld_pair(b + 2 * m) : hpv_dup(0.0f);
 #pragma unroll
         for (int c = 1; c < NCH; ++c) acc[c][m] = hpv_dup(0.0f);
     }
@@ -103,7 +103,7 @@ HPV_HD void hpv_matmul_slot(const float* W, const float* b, const float* slot, i
             for (int c = 0; c < NCH; ++c) xd[c] = hpv_dup(x[c][k]);
 #pragma unroll
             for (int m = 0; m < HP / 2; ++m) {
-                const hpv_pair w = hpv_pack(wr[2 * m], wr[2 * m + 1]);
+                const hpv_pair w = hpv_ld_pair(wr + 2 * m);      // every offset of the padded layout is even
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) hpv_fma2(acc[c][m], xd[c], w);
             }

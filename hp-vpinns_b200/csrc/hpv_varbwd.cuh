@@ -147,126 +147,150 @@ struct HpvBwdArgs {
     const float* pts;          // [n][dim] or null (then the points are the element quadrature points)
 };
 
+// Compact layout of a warp's gradient accumulator (the padded parameter layout of hpv_math.cuh without the
+// transposed copies):  [W1: DIM x HP][b1: HP] { [W_l: HP x HP][b_l: HP] } x (nhid-1) [Wo: HP][bo, 0, 0, 0]
+HPV_HD int hpv_gw_wl(int dim, int hp, int l /*1..nhid-1*/) { return (dim + 1) * hp + (l - 1) * (hp * hp + hp); }
+HPV_HD int hpv_gw_wo(int dim, int hp, int nhid) { return (dim + 1) * hp + (nhid - 1) * (hp * hp + hp); }
+HPV_HD int hpv_gw_n(int dim, int hp, int nhid) { return hpv_gw_wo(dim, hp, nhid) + hp + 4; }
+// padded index -> compact index, or -1 for the transposed copies (which carry no gradient)
+HPV_HD int hpv_gw_of_padded(int dim, int hp, int nhid, int ip) {
+    const int head = (dim + 1) * hp;
+    if (ip < head) return ip;
+    const int blk = 2 * hp * hp + hp, j = ip - head, l = j / blk;
+    if (l < nhid - 1) {
+        const int r = j - l * blk;
+        return r < hp * hp + hp ? head + l * (hp * hp + hp) + r : -1;
+    }
+    return head + (nhid - 1) * (hp * hp + hp) + (j - (nhid - 1) * blk);
+}
+
+// Shared-memory plan of the reverse sweep.  Everything but `cst` and `red` is private to a warp (its 32 slot rows
+// of every slot, its rows of in0/go, its own gradient accumulator): the warps of a CTA never wait for each other
+// inside the sweep.
 template <int DIM, int MX, int MY, int HP>
 struct HpvBwdSmem {
     typedef HpvMode<DIM, MX, MY> M;
     static constexpr int SP = HpvSP<HP>::value;
-    int gw, slots, in0, go, scratch, red, total, NS, slot_sz;
-    HPV_HD HpvBwdSmem(int theta_pad_n, int nhid, int T) {
+    static constexpr int NCH1 = 1 + (M::DX ? 1 : 0) + (M::DY ? 1 : 0);     // channels with a non-zero seed at layer 1
+    int cst, slots, in0, go, gw, red, total, NS, slot_sz, gwn;
+    HPV_HD HpvBwdSmem(int nhid, int T) {
         int o = 0;
-        gw = o; o += hpv_align4(theta_pad_n);
+        cst = o; o += 8;                                   // {1,0,0,0} (bias row of the value channel), {0,0,0,0}
         NS = nhid - 1 > 2 ? nhid - 1 : 2;
         slot_sz = M::NCH * T * SP;
         slots = o; o += NS * slot_sz;
-        in0 = o; o += 3 * T * 4;
-        go = o; o += M::NCH * T * 4;
-        scratch = o; o += T * 32;
+        in0 = o; o += NCH1 * T * 4;
+        go = o; o += hpv_align4(M::NCH * T);
+        gwn = hpv_gw_n(DIM, HP, nhid);
+        gw = o; o += (T / 32) * gwn;
         red = o; o += T;
         total = o;
     }
 };
 
-// Weight-gradient GEMM over the T points of a tile:  D[i][j] += sum_ch sum_p IN[ch][p][i] * ADJ[ch][p][j].
-// Register tile of 8 rows (i) x 4 columns (j) per thread, accumulated with packed FFMA2 over column pairs;
-// K (points) split over KS threads per tile, partials combined through shared memory in a fixed order
-// (deterministic).  Per point and channel a thread issues three 128-bit shared loads for 16 FFMA2.
-// NROWS = rows of IN (multiple of 4).  BIAS appends a virtual row of ones in the value channel (-> bias
-// gradient).  KIND: 0 hidden layer (dst = W[HP][HP], dstb = b), 1 output layer (dst = Wo[HP], dstb = bo; only
-// column 0 of ADJ is meaningful), 2 first layer (IN rows = x, y, 1, 0: dst = W1[DIM][HP], dstb = b1).
-template <int SPI, int SPA, int NCH, int NROWS, int NJ, bool BIAS, int KIND, int HP, int DIM>
-HPV_HD void hpv_wgrad_gemm(const HpvCta& c, const float* IN, const float* ADJ, float* dst, float* dstb, float* scratch) {
-    constexpr int RTOT = NROWS + (BIAS ? 1 : 0);
-    constexpr int NI = (RTOT + 7) / 8;
+// Weight-gradient GEMM over the 32 points of ONE warp:  D[i][j] += sum_ch sum_p IN[ch][p][i] * ADJ[ch][p][j].
+// A lane owns a register tile of 4 rows (i) x TN columns (j), TN = 4 (two packed pairs per row) or 1 (output
+// layer: ADJ is one scalar per point and channel).  With fewer tiles than lanes the points (K) are split over
+// KSW lanes per tile and the partial tiles are summed with xor-shuffles (fixed order, deterministic); with more
+// tiles than lanes (HP = 32) a lane takes several tiles in turn.  The loop body is uniform: a row group beyond
+// the rows of IN reads a constant vector instead -- {1,0,0,0} for the bias row in the value channel, zeros
+// otherwise -- with stride 0, so there is no per-point branching.  D is this warp's private accumulator in
+// shared memory; nothing here synchronises with other warps.
+//   KIND 0: hidden layer, D = W[HP][HP], bias row -> b (= W + HP*HP).   KIND 1: output layer, D = Wo[HP] followed
+//   by (bo, 0, 0, 0), TN = 1.   KIND 2: first layer, IN rows = (x, y, 1, 0): rows < DIM -> W1, row 2 -> b1.
+template <int SPI, int SPA, int NCH, int NROWS, int NJ, int TN, bool BIAS, int KIND, int HP, int DIM>
+HPV_HD void hpv_wgrad_warp(const HpvCta& c, const float* IN, const float* ADJ, float* D, float* Db, const float* cst) {
+    constexpr int NI = (NROWS + (BIAS ? 1 : 0) + 3) / 4;
     constexpr int NTILES = NI * NJ;
-    const int T = c.nthreads, tid = c.tid;
-    int KS = 1;
-    while (KS * 2 * NTILES <= T) KS *= 2;
-    const int tau = tid / KS, ks = tid - tau * KS;
-    const bool active = tau < NTILES;
-    const int it = active ? tau / NJ : 0, jt = active ? tau - it * NJ : 0;
-    // the two 4-row groups of this thread's tile: 0 = rows of IN, 1 = the bias row (ones) first, 2 = empty
-    const int r0 = 8 * it, r1 = 8 * it + 4;
-    const int ty0 = r0 < NROWS ? 0 : ((BIAS && r0 == NROWS) ? 1 : 2);
-    const int ty1 = r1 < NROWS ? 0 : ((BIAS && r1 == NROWS) ? 1 : 2);
-    hpv_pair acc[8][2];
+    constexpr int KSW = NTILES > 16 ? 1 : (NTILES > 8 ? 2 : (NTILES > 4 ? 4 : (NTILES > 2 ? 8 : 16)));
+    constexpr int TPB = 32 / KSW;                          // tiles per batch
+    constexpr int NP = TN == 4 ? 2 : 1;                    // packed pairs per accumulator row (TN = 1: rows are paired)
+    const int T = c.nthreads, lane = c.tid & 31, wbase = c.tid & ~31;
+    const int ks = lane % KSW;
+#pragma unroll 1
+    for (int tb = 0; tb < NTILES; tb += TPB) {
+        const int tau = tb + lane / KSW;
+        const bool active = tau < NTILES;
+        const int it = active ? tau / NJ : 0, jt = active ? tau - it * NJ : 0;
+        const int r0 = 4 * it;
+        const int ty = r0 < NROWS ? 0 : ((BIAS && r0 == NROWS) ? 1 : 2);
+        hpv_pair acc[4][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { acc[i][0] = hpv_pack(0.0f, 0.0f); acc[i][1] = hpv_pack(0.0f, 0.0f); }
-    if (active) {
+        for (int i = 0; i < 4; ++i) { acc[i][0] = hpv_dup(0.0f); acc[i][1] = hpv_dup(0.0f); }
+        if (active) {
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-            const float* pa0 = IN + (size_t)ch * T * SPI + ks * SPI + r0;
-            const float* pa1 = pa0 + 4;
-            const float* pb = ADJ + (size_t)ch * T * SPA + ks * SPA + 4 * jt;
-            const int sa = KS * SPI, sb = KS * SPA;
-            const float one = (ch == 0) ? 1.0f : 0.0f;
-            const int niter = (T - ks + KS - 1) / KS;
-#pragma unroll 4
-            for (int it2 = 0; it2 < niter; ++it2) {
-                HpvF4 a0, a1;
-                a0.x = one; a0.y = a0.z = a0.w = 0.0f;
-                a1 = a0;
-                if (ty0 == 0) a0 = hpv_ld4(pa0);
-                else if (ty0 == 2) a0.x = 0.0f;
-                if (ty1 == 0) a1 = hpv_ld4(pa1);
-                else if (ty1 == 2) a1.x = 0.0f;
-                const HpvF4 b4 = hpv_ld4(pb);
-                pa0 += sa; pa1 += sa; pb += sb;
-                const hpv_pair b01 = hpv_pack(b4.x, b4.y), b23 = hpv_pack(b4.z, b4.w);
-                const float as[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            for (int ch = 0; ch < NCH; ++ch) {
+                const float* pa = (ty == 0) ? IN + ((size_t)ch * T + wbase + ks) * SPI + r0 : ((ty == 1 && ch == 0) ? cst : cst + 4);
+                const int sa = (ty == 0) ? KSW * SPI : 0;
+                const float* pb = ADJ + ((size_t)ch * T + wbase + ks) * SPA + (TN == 4 ? 4 * jt : 0);
+#pragma unroll 8
+                for (int k = 0; k < 32 / KSW; ++k) {
+                    const HpvF4 a4 = hpv_ld4(pa);
+                    pa += sa;
+                    if constexpr (TN == 4) {
+                        const HpvF4 b4 = hpv_ld4(pb);
+                        const hpv_pair b01 = hpv_pack(b4.x, b4.y), b23 = hpv_pack(b4.z, b4.w);
+                        const float as[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const hpv_pair ad = hpv_dup(as[i]);
-                    hpv_fma2(acc[i][0], ad, b01);
-                    hpv_fma2(acc[i][1], ad, b23);
+                        for (int i = 0; i < 4; ++i) {
+                            const hpv_pair ad = hpv_dup(as[i]);
+                            hpv_fma2(acc[i][0], ad, b01);
+                            hpv_fma2(acc[i][1], ad, b23);
+                        }
+                    } else {
+                        const hpv_pair bd = hpv_dup(pb[0]);
+                        hpv_fma2(acc[0][0], hpv_pack(a4.x, a4.y), bd);
+                        hpv_fma2(acc[1][0], hpv_pack(a4.z, a4.w), bd);
+                    }
+                    pb += KSW * SPA;
                 }
             }
         }
-    }
-    float out[8][4];
+        // sum the KSW partial tiles (all lanes take part in the exchanges)
+        float v[4][4];
+        if constexpr (TN == 4) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { hpv_unpack(acc[i][0], out[i][0], out[i][1]); hpv_unpack(acc[i][1], out[i][2], out[i][3]); }
-    // Combine the KS partial tiles through shared memory.  Every thread of a tile's group takes part: thread ks
-    // sums rows ks, ks+KS, ... of the 8-row tile over the KS partials in a fixed order (deterministic), and adds
-    // them to the accumulated gradient.
-    if (KS > 1) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            HpvF4 o; o.x = out[i][0]; o.y = out[i][1]; o.z = out[i][2]; o.w = out[i][3];
-            hpv_st4(scratch + tid * 32 + 4 * i, o);
+            for (int i = 0; i < 4; ++i) { hpv_unpack(acc[i][0], v[i][0], v[i][1]); hpv_unpack(acc[i][1], v[i][2], v[i][3]); }
+        } else {
+            hpv_unpack(acc[0][0], v[0][0], v[1][0]);
+            hpv_unpack(acc[1][0], v[2][0], v[3][0]);
         }
-        hpv_sync(c);
-    }
-    if (active) {
-        const float* grp = scratch + (size_t)(tid - ks) * 32;
-        for (int i = ks; i < 8; i += KS) {
-            float v[4];
-            if (KS > 1) {
-                HpvF4 s4 = hpv_ld4(grp + 4 * i);
-                for (int s = 1; s < KS; ++s) {
-                    const HpvF4 t4 = hpv_ld4(grp + s * 32 + 4 * i);
-                    s4.x += t4.x; s4.y += t4.y; s4.z += t4.z; s4.w += t4.w;
-                }
-                v[0] = s4.x; v[1] = s4.y; v[2] = s4.z; v[3] = s4.w;
+#pragma unroll
+        for (int m = 1; m < KSW; m <<= 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < (TN == 4 ? 4 : 1); ++j) v[i][j] += hpv_shfl_xor(c, v[i][j], m);
+        }
+        (void)NP;
+        if (active && ks == 0) {
+            if constexpr (KIND == 1) {
+                // rows r0 .. r0+3 of (Wo[0..HP-1], bo, 0, 0, 0) are contiguous
+                HpvF4 d = hpv_ld4(D + r0);
+                d.x += v[0][0]; d.y += v[1][0]; d.z += v[2][0]; d.w += v[3][0];
+                hpv_st4(D + r0, d);
             } else {
 #pragma unroll
-                for (int i2 = 0; i2 < 8; ++i2)
-                    if (i2 == i) { v[0] = out[i2][0]; v[1] = out[i2][1]; v[2] = out[i2][2]; v[3] = out[i2][3]; }
-            }
-            const int r = 8 * it + i;
-            if (KIND == 0) {
-                if (r < NROWS) { for (int j = 0; j < 4; ++j) dst[r * HP + 4 * jt + j] += v[j]; }
-                else if (BIAS && r == NROWS) { for (int j = 0; j < 4; ++j) dstb[4 * jt + j] += v[j]; }
-            } else if (KIND == 1) {
-                if (r < NROWS) dst[r] += v[0];
-                else if (BIAS && r == NROWS) dstb[0] += v[0];
-            } else {
-                if (r < DIM) { for (int j = 0; j < 4; ++j) dst[r * HP + 4 * jt + j] += v[j]; }
-                else if (r == 2) { for (int j = 0; j < 4; ++j) dstb[4 * jt + j] += v[j]; }
+                for (int i = 0; i < 4; ++i) {
+                    const int r = r0 + i;
+                    float* row = nullptr;
+                    if (KIND == 0) row = r < NROWS ? D + r * HP : ((BIAS && r == NROWS) ? Db : nullptr);
+                    else row = r < DIM ? D + r * HP : (r == 2 ? Db : nullptr);
+                    if (row) {
+                        HpvF4 d = hpv_ld4(row + 4 * jt);
+                        d.x += v[i][0]; d.y += v[i][1]; d.z += v[i][2]; d.w += v[i][3];
+                        hpv_st4(row + 4 * jt, d);
+                    }
+                }
             }
         }
     }
 }
 
+// The reverse sweep.  A warp takes a contiguous range of 32-point tiles and runs, per tile and without waiting
+// for any other warp: forward recompute (pre-activations kept in the slots), output-layer gradient, then per
+// hidden layer top-down the activation adjoint, the weight-gradient GEMM over the warp's points and the
+// adjoint product one layer down (transposed weights, the forward product loop), and the first-layer gradient.
 template <int DIM, int MX, int MY, int HP, int ACT>
 HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
     typedef HpvMode<DIM, MX, MY> M;
@@ -274,13 +298,14 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
     constexpr int SP = HpvSP<HP>::value;
     const HpvVarArgs& a = ba.v;
     const int T = c.nthreads, tid = c.tid, nhid = a.nhid, top = nhid - 1;
-    const HpvBwdSmem<DIM, MX, MY, HP> L(a.theta_pad_n, nhid, T);
+    const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    const HpvBwdSmem<DIM, MX, MY, HP> L(nhid, T);
     float* sm = reinterpret_cast<float*>(c.smem);
     const float* s_th = HPV_THETA(a.theta_pad);
-    float* s_gw = sm + L.gw;
+    float* s_cst = sm + L.cst;
+    float* s_gw = sm + L.gw + (size_t)warp * L.gwn;          // this warp's gradient accumulator (compact layout)
     float* s_in0 = sm + L.in0;
     float* s_go = sm + L.go;
-    float* s_scr = sm + L.scratch;
     float* s_red = sm + L.red;
     // Slots (one row of SP floats per thread and channel).  P(l), l = 1..top-1: pre-activations of hidden layer l
     // kept from the forward recompute, later overwritten by the post-activations (left factor of the W_{l+1}
@@ -291,7 +316,8 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
     float* const H0 = sm + L.slots + (size_t)(top >= 2 ? 0 : 1) * L.slot_sz;
 #define HPV_P(l) (sm + L.slots + (size_t)((l) - 1) * L.slot_sz)
 
-    for (int i = tid; i < a.theta_pad_n; i += T) s_gw[i] = 0.0f;
+    for (int i = lane; i < L.gwn; i += 32) s_gw[i] = 0.0f;
+    if (tid < 8) s_cst[tid] = (tid == 0) ? 1.0f : 0.0f;
     const float eps = a.eps[0];
     float coef[HPV_MAX_TERMS][HPV_NFIELDS], coef1[HPV_MAX_TERMS][HPV_NFIELDS];
     for (int t = 0; t < HPV_MAX_TERMS; ++t)
@@ -303,14 +329,23 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
 
     const int Q = a.Q, npts_el = a.rows * Q;
     float deps = 0.0f;
-    const int tile_begin = (int)(((long long)c.bid * ba.n_tiles) / c.nblocks);
-    const int tile_end = (int)(((long long)(c.bid + 1) * ba.n_tiles) / c.nblocks);
+    // Work partition: groups of nwarps consecutive 32-point tiles, a contiguous range of groups per CTA, tile
+    // (group, warp) to warp `warp`.  The trip count is the same for every warp of the CTA -- the loop control
+    // stays in the uniform datapath, which the constant-memory weight loads of the products below depend on
+    // (with per-warp trip counts the compiler falls back to vector-indexed LDC) -- and only the last group of the
+    // launch can hold tiles without points (they run with zero adjoints, like the padding points of a tile).
+    const long long n_wt = ((long long)ba.n_points + 31) / 32;
+    const long long n_grp = (n_wt + nwarps - 1) / nwarps;
+    const int grp_begin = (int)(((long long)c.bid * n_grp) / c.nblocks);
+    const int grp_end = (int)(((long long)(c.bid + 1) * n_grp) / c.nblocks);
     const float* Wo = s_th + a.off_wo;
+    const int g_wo = hpv_gw_wo(DIM, HP, nhid);
 
 #pragma unroll 1
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const int gp = tile * T + tid;
-        const bool valid = gp < ba.n_points;
+    for (int grp = grp_begin; grp < grp_end; ++grp) {
+        const long long gpl = ((long long)grp * nwarps + warp) * 32 + lane;
+        const bool valid = gpl < (long long)ba.n_points;
+        const int gp = valid ? (int)gpl : 0;
         float x = 0.0f, y = 0.0f;
         float gbar[HPV_MAX_TERMS] = {0.0f, 0.0f};
         if (valid) {
@@ -373,27 +408,23 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
         }
 
         // ---- output layer: Wo/bo gradient (left factor h_top in X), adjoint of h_top ----
-        {
-            HpvF4 o; o.y = o.z = o.w = 0.0f;
-            o.x = gf[0]; hpv_st4(s_go + (M::C_V * T + tid) * 4, o);
-            if constexpr (M::DX) { o.x = gf[1]; hpv_st4(s_go + (M::C_DX * T + tid) * 4, o); }
-            if constexpr (M::DY) { o.x = gf[2]; hpv_st4(s_go + (M::C_DY * T + tid) * 4, o); }
-            if constexpr (M::EX) { o.x = gf[3]; hpv_st4(s_go + (M::C_EX * T + tid) * 4, o); }
-            if constexpr (M::EY) { o.x = gf[4]; hpv_st4(s_go + (M::C_EY * T + tid) * 4, o); }
-        }
+        s_go[M::C_V * T + tid] = gf[0];
+        if constexpr (M::DX) s_go[M::C_DX * T + tid] = gf[1];
+        if constexpr (M::DY) s_go[M::C_DY * T + tid] = gf[2];
+        if constexpr (M::EX) s_go[M::C_EX * T + tid] = gf[3];
+        if constexpr (M::EY) s_go[M::C_EY * T + tid] = gf[4];
 #pragma unroll
         for (int m = 0; m < HP / 2; ++m) {
-            const hpv_pair w = hpv_pack(Wo[2 * m], Wo[2 * m + 1]);
+            const hpv_pair w = hpv_ld_pair(Wo + 2 * m);
             g.v.p[m] = hpv_mul2(hpv_dup(gf[0]), w);
             if constexpr (M::DX) g.dx.p[m] = hpv_mul2(hpv_dup(gf[1]), w);
             if constexpr (M::DY) g.dy.p[m] = hpv_mul2(hpv_dup(gf[2]), w);
             if constexpr (M::EX) g.ex.p[m] = hpv_mul2(hpv_dup(gf[3]), w);
             if constexpr (M::EY) g.ey.p[m] = hpv_mul2(hpv_dup(gf[4]), w);
         }
-        hpv_sync(c);
-        hpv_wgrad_gemm<SP, 4, M::NCH, HP, 1, true, 1, HP, DIM>(c, X, s_go, s_gw + a.off_wo,
-                                                                s_gw + a.off_wo + HP, s_scr);
-        hpv_sync(c);
+        hpv_syncwarp(c);
+        hpv_wgrad_warp<SP, 1, M::NCH, HP, 1, 1, true, 1, HP, DIM>(c, X, s_go, s_gw + g_wo, nullptr, s_cst);
+        hpv_syncwarp(c);
 
         // ---- hidden layers, top down ----
         int woff_t = a.off_wo - HP * HP;                             // = hpv_off_wt(DIM, HP, top)
@@ -409,10 +440,10 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
                 hpv_activate<DIM, MX, MY, HP, ACT>(h);                  // h_{l-1}: left factor of the W_l gradient
                 hpv_store_state<DIM, MX, MY, HP>(INl, T, tid, h);
             }
-            hpv_sync(c);
-            float* gW = s_gw + hpv_off_wl(DIM, HP, l);
-            hpv_wgrad_gemm<SP, SP, M::NCH, HP, HP / 4, true, 0, HP, DIM>(c, INl, X, gW, gW + HP * HP, s_scr);
-            hpv_sync(c);
+            hpv_syncwarp(c);
+            float* gW = s_gw + hpv_gw_wl(DIM, HP, l);
+            hpv_wgrad_warp<SP, SP, M::NCH, HP, HP / 4, 4, true, 0, HP, DIM>(c, INl, X, gW, gW + HP * HP, s_cst);
+            hpv_syncwarp(c);
             // adjoint of h_{l-1} = ADJ_l . W_l^T: the forward product loop on the transposed copy, inputs from X
             hpv_matmul_slot<DIM, MX, MY, HP, false>(s_th + woff_t, nullptr, X, T, tid, g);
         }
@@ -426,29 +457,34 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
             if constexpr (M::DIR) {                    // the tangent seed is v . W1: its left factor is v
                 o.x = vx; o.y = vy; o.z = 0.0f; o.w = 0.0f; hpv_st4(s_in0 + (1 * T + tid) * 4, o);
             } else {
-                o.x = 1.0f; o.y = 0.0f; o.z = 0.0f; o.w = 0.0f; hpv_st4(s_in0 + (1 * T + tid) * 4, o);
-                o.x = 0.0f; o.y = 1.0f; hpv_st4(s_in0 + (2 * T + tid) * 4, o);
+                if constexpr (M::DX) { o.x = 1.0f; o.y = 0.0f; o.z = 0.0f; o.w = 0.0f; hpv_st4(s_in0 + (M::C_DX * T + tid) * 4, o); }
+                if constexpr (M::DY) { o.x = 0.0f; o.y = 1.0f; o.z = 0.0f; o.w = 0.0f; hpv_st4(s_in0 + (M::C_DY * T + tid) * 4, o); }
             }
         }
-        hpv_sync(c);
+        hpv_syncwarp(c);
         // channels that feed W1: value (x, y, 1), d/dx (1, 0, 0), d/dy (0, 1, 0); second-derivative seeds are 0.
         // The IN rows are ordered v, dx, dy, which is also the order of the stored channels (C_V, C_DX, C_DY).
         {
-            float* gW1 = s_gw + hpv_off_w1();
-            float* gb1 = s_gw + hpv_off_b1(DIM, HP);
-            constexpr int nch1 = 1 + (M::DX ? 1 : 0) + (M::DY ? 1 : 0);
-            hpv_wgrad_gemm<4, SP, nch1, 4, HP / 4, false, 2, HP, DIM>(c, s_in0, X, gW1, gb1, s_scr);
-            hpv_sync(c);
+            constexpr int nch1 = HpvBwdSmem<DIM, MX, MY, HP>::NCH1;
+            hpv_wgrad_warp<4, SP, nch1, 4, HP / 4, 4, false, 2, HP, DIM>(c, s_in0, X, s_gw, s_gw + DIM * HP, s_cst);
+            hpv_syncwarp(c);
         }
 #undef HPV_LAYER1
     }
 #undef HPV_P
 
-    // ---- publish this CTA's partial gradient ----
+    // ---- publish this CTA's partial gradient: the warps' accumulators summed in a fixed order, padded layout ----
     const float dtot = hpv_block_sum(c, s_red, deps);
-    float* gp = a.grad_part + (size_t)c.bid * a.grad_stride;
-    for (int i = tid; i < a.theta_pad_n; i += T) gp[i] = s_gw[i];
-    if (tid == 0) gp[a.theta_pad_n] = dtot;
+    float* gpart = a.grad_part + (size_t)c.bid * a.grad_stride;
+    const float* gw0 = sm + L.gw;
+    for (int ip = tid; ip < a.theta_pad_n; ip += T) {
+        const int ic = hpv_gw_of_padded(DIM, HP, nhid, ip);
+        float sum = 0.0f;
+        if (ic >= 0)
+            for (int w = 0; w < nwarps; ++w) sum += gw0[(size_t)w * L.gwn + ic];
+        gpart[ip] = sum;
+    }
+    if (tid == 0) gpart[a.theta_pad_n] = dtot;
 }
 
 // K3: grad_pad[i] (+)= sum over CTAs of grad_part[c][i], fixed order.  One CTA of 256 threads = 32 entries x 8

@@ -5,6 +5,7 @@
 // or loads this file; the product has no CPU path.
 #include <barrier>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -12,8 +13,20 @@
 #include "../../hp-vpinns_b200/csrc/hpv_varbwd.cuh"
 #include "../../hp-vpinns_b200/csrc/hpv_points.cuh"
 
-struct HpvEmu { std::barrier<>* bar; };
+struct HpvEmu {
+    std::barrier<>* bar;                 // the CTA barrier (__syncthreads)
+    std::barrier<>** wbar;               // one barrier per warp (__syncwarp, shuffles)
+    float* xchg;                         // [threads] exchange buffer of the emulated shuffles
+};
 void hpv_emu_barrier(HpvEmu* e) { e->bar->arrive_and_wait(); }
+void hpv_emu_warp_barrier(HpvEmu* e, int warp) { e->wbar[warp]->arrive_and_wait(); }
+float hpv_emu_shfl_xor(HpvEmu* e, int tid, float v, int mask) {
+    e->xchg[tid] = v;
+    e->wbar[tid >> 5]->arrive_and_wait();
+    const float r = e->xchg[tid ^ mask];
+    e->wbar[tid >> 5]->arrive_and_wait();
+    return r;
+}
 
 namespace {
 
@@ -24,7 +37,16 @@ void run_grid(int grid, int block, size_t smem_bytes, Body body) {
     sm += (16 - (reinterpret_cast<uintptr_t>(sm) & 15)) & 15;
     for (int b = 0; b < grid; ++b) {
         std::barrier<> bar(block);
-        HpvEmu emu{&bar};
+        const int nw = (block + 31) / 32;
+        std::vector<std::unique_ptr<std::barrier<>>> wb;
+        std::vector<std::barrier<>*> wbp;
+        for (int w = 0; w < nw; ++w) {
+            const int n = (w + 1) * 32 <= block ? 32 : block - w * 32;
+            wb.emplace_back(new std::barrier<>(n));
+            wbp.push_back(wb.back().get());
+        }
+        std::vector<float> xchg(block, 0.0f);
+        HpvEmu emu{&bar, wbp.data(), xchg.data()};
         std::vector<std::thread> th;
         th.reserve(block);
         for (int t = 0; t < block; ++t) {
@@ -68,7 +90,7 @@ int emu_fwd(const Key& k, const HpvVarArgs& a, int grid, size_t smem) {
 int emu_bwd(const Key& k, const HpvBwdArgs& a, int grid, int block) {
 #define CALL(DIM, MX, MY, HP, ACT)                                                                       \
     {                                                                                                    \
-        HpvBwdSmem<DIM, MX, MY, HP> L(a.v.theta_pad_n, a.v.nhid, block);                                 \
+        HpvBwdSmem<DIM, MX, MY, HP> L(a.v.nhid, block);                                 \
         run_grid(grid, block, (size_t)L.total * 4, [&](const HpvCta& c) { hpv_mlpbwd_body<DIM, MX, MY, HP, ACT>(c, a); }); \
     }
     if (k.dim == 2 && k.mx == 1 && k.my == 1 && g_bwd_dir && a.pts == nullptr) {
