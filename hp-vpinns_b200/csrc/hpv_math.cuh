@@ -164,15 +164,45 @@ HPV_HD void hpv_act2(hpv_pair z, hpv_pair& a, hpv_pair& s1, hpv_pair& s2, hpv_pa
     }
 }
 
-// Pre-activations (z, dz, d2z) -> post-activations (h, dh, d2h), in place, on packed pairs of units.
-//   h = s(z);  dh = s'(z) dz;  d2h = s''(z) dz^2 + s'(z) d2z
+// "Mixed" state of a layer, the form the reverse sweep keeps: the tangent channels as pre-activations (dz, d2z),
+// the value channel as the pre-activation z for sin, but as the POST-activation a = tanh z for tanh -- every
+// derivative of tanh is a polynomial in a (s1 = 1 - a^2, s2 = -2 a s1, s3 = -2 s1 (1 - 3 a^2)), so whatever is
+// derived from a mixed state later costs no second exp/reciprocal.
 template <int DIM, int MX, int MY, int HP, int ACT>
+HPV_HD void hpv_to_mixed(HpvState<DIM, MX, MY, HP>& s) {
+    if constexpr (ACT == HPV_ACT_TANH) {
+#pragma unroll
+        for (int m = 0; m < HP / 2; ++m) {
+            hpv_pair a, s1;
+            hpv_tanh2(s.v.p[m], a, s1);
+            s.v.p[m] = a;
+        }
+    }
+}
+
+// Activation value and derivatives of a pair of units from the value channel of a plain (MIXED = false:
+// pre-activation) or mixed state.
+template <int ACT, bool MIXED>
+HPV_HD void hpv_act2m(hpv_pair zv, hpv_pair& a, hpv_pair& s1, hpv_pair& s2, hpv_pair& s3, bool need3) {
+    if constexpr (MIXED && ACT == HPV_ACT_TANH) {
+        a = zv;
+        s1 = hpv_fma2r(hpv_mul2(a, a), hpv_dup(-1.0f), hpv_dup(1.0f));
+        s2 = hpv_mul2(hpv_mul2(a, s1), hpv_dup(-2.0f));
+        if (need3) s3 = hpv_mul2(hpv_mul2(s1, hpv_fma2r(hpv_mul2(a, a), hpv_dup(-3.0f), hpv_dup(1.0f))), hpv_dup(-2.0f));
+    } else {
+        hpv_act2<ACT>(zv, a, s1, s2, s3, need3);
+    }
+}
+
+// Pre-activations (z, dz, d2z) [or a mixed state] -> post-activations (h, dh, d2h), in place, on packed pairs.
+//   h = s(z);  dh = s'(z) dz;  d2h = s''(z) dz^2 + s'(z) d2z
+template <int DIM, int MX, int MY, int HP, int ACT, bool MIXED = false>
 HPV_HD void hpv_activate(HpvState<DIM, MX, MY, HP>& s) {
     typedef HpvMode<DIM, MX, MY> M;
 #pragma unroll
     for (int m = 0; m < HP / 2; ++m) {
         hpv_pair a, s1, s2, s3;
-        hpv_act2<ACT>(s.v.p[m], a, s1, s2, s3, false);
+        hpv_act2m<ACT, MIXED>(s.v.p[m], a, s1, s2, s3, false);
         s.v.p[m] = a;
         if constexpr (M::DX) {
             const hpv_pair dz = s.dx.p[m];
@@ -193,13 +223,14 @@ HPV_HD void hpv_activate(HpvState<DIM, MX, MY, HP>& s) {
 //   dzbar  = dhbar s1 + 2 d2hbar s2 dz
 //   d2zbar = d2hbar s1
 // with s1, s2, s3 the first three derivatives of the activation at z (tanh: s2 = -2 a s1, s3 = -2 s1 (1 - 3 a^2)).
-template <int DIM, int MX, int MY, int HP, int ACT>
+// MIXED: z is a mixed state (see hpv_to_mixed).
+template <int DIM, int MX, int MY, int HP, int ACT, bool MIXED = false>
 HPV_HD void hpv_activate_bwd(const HpvState<DIM, MX, MY, HP>& z, HpvState<DIM, MX, MY, HP>& g) {
     typedef HpvMode<DIM, MX, MY> M;
 #pragma unroll
     for (int m = 0; m < HP / 2; ++m) {
         hpv_pair a, s1, s2, s3;
-        hpv_act2<ACT>(z.v.p[m], a, s1, s2, s3, M::EX || M::EY);
+        hpv_act2m<ACT, MIXED>(z.v.p[m], a, s1, s2, s3, M::EX || M::EY);
         hpv_pair zb = hpv_mul2(g.v.p[m], s1);
         if constexpr (M::DX) {
             const hpv_pair dz = z.dx.p[m], gd = g.dx.p[m];

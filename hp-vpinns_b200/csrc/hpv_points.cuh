@@ -27,7 +27,9 @@ HPV_HD void hpv_points_body(const HpvCta& c, const HpvPointArgs& a, float* gbar_
             const float x = a.pts[(size_t)i * DIM];
             const float y = (DIM == 2) ? a.pts[(size_t)i * DIM + 1] : 0.0f;
             float f[HPV_NFIELDS];
-            hpv_net_point_slot<DIM, MX, MY, HP, ACT>(th, a.nhid, a.off_wo, x, y, s_slot, T, tid, f);
+            hpv_net_point_slot<DIM, MX, MY, HP, ACT>(th, a.nhid, a.off_wo, x, y,
+                                                     s_slot + (tid >> 5) * (HpvMode<DIM, MX, MY>::NCH * 32 * HpvSP<HP>::value),
+                                                     32, tid & 31, f);
             if (a.out_u) a.out_u[i] = f[0];
             if (a.out_d1) { a.out_d1[(size_t)i * DIM] = f[1]; if (DIM == 2) a.out_d1[(size_t)i * DIM + 1] = f[2]; }
             if (a.out_d2) { a.out_d2[(size_t)i * DIM] = f[3]; if (DIM == 2) a.out_d2[(size_t)i * DIM + 1] = f[4]; }

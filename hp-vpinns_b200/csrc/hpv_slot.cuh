@@ -83,6 +83,7 @@ HPV_HD void hpv_matmul_slot(const float* W, const float* b, const float* slot, i
 #pragma unroll
         for (int c = 1; c < NCH; ++c) acc[c][m] = hpv_dup(0.0f);
     }
+    static_assert(HP % 4 == 0, "padded hidden width must be a multiple of 4 (128-bit weight loads)");
     // two independent induction variables: the weight pointer (constant memory, must stay in uniform registers so
     // that the loads are LDCU and the FFMA2 take a UR operand) and the slot-row pointer (per-thread, vector)
     const float* row = slot + (size_t)tid * SP;
@@ -102,10 +103,13 @@ HPV_HD void hpv_matmul_slot(const float* W, const float* b, const float* slot, i
 #pragma unroll
             for (int c = 0; c < NCH; ++c) xd[c] = hpv_dup(x[c][k]);
 #pragma unroll
-            for (int m = 0; m < HP / 2; ++m) {
-                const hpv_pair w = hpv_ld_pair(wr + 2 * m);      // every offset of the padded layout is even
+            for (int m4 = 0; m4 < HP / 4; ++m4) {
+                // four weights per load (constant memory: one LDCU.128 feeding 2 * NCH FFMA2); every offset of the
+                // padded layout is a multiple of 4 floats
+                hpv_pair w0, w1;
+                hpv_ld_pairs(wr + 4 * m4, w0, w1);
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) hpv_fma2(acc[c][m], xd[c], w);
+                for (int c = 0; c < NCH; ++c) { hpv_fma2(acc[c][2 * m4], xd[c], w0); hpv_fma2(acc[c][2 * m4 + 1], xd[c], w1); }
             }
         }
     }

@@ -188,7 +188,8 @@ struct HpvBwdSmem {
     }
 };
 
-// Weight-gradient GEMM over the 32 points of ONE warp:  D[i][j] += sum_ch sum_p IN[ch][p][i] * ADJ[ch][p][j].
+// Weight-gradient GEMM over the 32 points of ONE warp:  D[i][j] += sum_ch sum_p IN[ch][p][i] * ADJ[ch][p][j],
+// IN and ADJ being the warp's own blocks [channel][32 points][SPI | SPA].
 // A lane owns a register tile of 4 rows (i) x TN columns (j), TN = 4 (two packed pairs per row) or 1 (output
 // layer: ADJ is one scalar per point and channel).  With fewer tiles than lanes the points (K) are split over
 // KSW lanes per tile and the partial tiles are summed with xor-shuffles (fixed order, deterministic); with more
@@ -205,7 +206,7 @@ HPV_HD void hpv_wgrad_warp(const HpvCta& c, const float* IN, const float* ADJ, f
     constexpr int KSW = NTILES > 16 ? 1 : (NTILES > 8 ? 2 : (NTILES > 4 ? 4 : (NTILES > 2 ? 8 : 16)));
     constexpr int TPB = 32 / KSW;                          // tiles per batch
     constexpr int NP = TN == 4 ? 2 : 1;                    // packed pairs per accumulator row (TN = 1: rows are paired)
-    const int T = c.nthreads, lane = c.tid & 31, wbase = c.tid & ~31;
+    const int lane = c.tid & 31;
     const int ks = lane % KSW;
 #pragma unroll 1
     for (int tb = 0; tb < NTILES; tb += TPB) {
@@ -220,9 +221,9 @@ HPV_HD void hpv_wgrad_warp(const HpvCta& c, const float* IN, const float* ADJ, f
         if (active) {
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
-                const float* pa = (ty == 0) ? IN + ((size_t)ch * T + wbase + ks) * SPI + r0 : ((ty == 1 && ch == 0) ? cst : cst + 4);
+                const float* pa = (ty == 0) ? IN + (ch * 32 + ks) * SPI + r0 : ((ty == 1 && ch == 0) ? cst : cst + 4);
                 const int sa = (ty == 0) ? KSW * SPI : 0;
-                const float* pb = ADJ + ((size_t)ch * T + wbase + ks) * SPA + (TN == 4 ? 4 * jt : 0);
+                const float* pb = ADJ + (ch * 32 + ks) * SPA + (TN == 4 ? 4 * jt : 0);
 #pragma unroll 8
                 for (int k = 0; k < 32 / KSW; ++k) {
                     const HpvF4 a4 = hpv_ld4(pa);
@@ -304,23 +305,32 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
     const float* s_th = HPV_THETA(a.theta_pad);
     float* s_cst = sm + L.cst;
     float* s_gw = sm + L.gw + (size_t)warp * L.gwn;          // this warp's gradient accumulator (compact layout)
-    float* s_in0 = sm + L.in0;
-    float* s_go = sm + L.go;
+    // Every per-point buffer is laid out [warp][channel][32 lanes][...]: a warp addresses its own block with
+    // compile-time strides (the slot helpers are called with T = 32, tid = lane).
+    constexpr int NCH1 = HpvBwdSmem<DIM, MX, MY, HP>::NCH1;
+    constexpr int WSLOT = M::NCH * 32 * SP;
+    float* s_in0 = sm + L.in0 + warp * (NCH1 * 32 * 4);
+    float* s_go = sm + L.go + warp * (M::NCH * 32);
     float* s_red = sm + L.red;
     // Slots (one row of SP floats per thread and channel).  P(l), l = 1..top-1: pre-activations of hidden layer l
     // kept from the forward recompute, later overwritten by the post-activations (left factor of the W_{l+1}
     // gradient).  X: the running slot -- post-activations feeding the next layer product, then the adjoint of
     // the pre-activations of the layer being differentiated, then (in place) the adjoint handed one layer down.
     // H0: post-activations of the first hidden layer (recomputed), in a slot that is dead by then.
-    float* const X = sm + L.slots + (size_t)(top >= 1 ? top - 1 : 0) * L.slot_sz;
-    float* const H0 = sm + L.slots + (size_t)(top >= 2 ? 0 : 1) * L.slot_sz;
-#define HPV_P(l) (sm + L.slots + (size_t)((l) - 1) * L.slot_sz)
+    // With tanh the kept states are "mixed" (hpv_to_mixed): nothing in the reverse part evaluates tanh again
+    // except for the first hidden layer, whose state is rebuilt from the coordinates.
+    float* const slots_w = sm + L.slots + warp * WSLOT;
+    float* const X = slots_w + (size_t)(top >= 1 ? top - 1 : 0) * L.slot_sz;
+    float* const H0 = slots_w + (size_t)(top >= 2 ? 0 : 1) * L.slot_sz;
+#define HPV_P(l) (slots_w + (size_t)((l) - 1) * L.slot_sz)
 
     for (int i = lane; i < L.gwn; i += 32) s_gw[i] = 0.0f;
     if (tid < 8) s_cst[tid] = (tid == 0) ? 1.0f : 0.0f;
     const float eps = a.eps[0];
-    float coef[HPV_MAX_TERMS][HPV_NFIELDS], coef1[HPV_MAX_TERMS][HPV_NFIELDS];
+    float coef[HPV_MAX_TERMS][HPV_NFIELDS], coef1[HPV_MAX_TERMS][HPV_NFIELDS];      // registers: every loop over them is unrolled
+#pragma unroll
     for (int t = 0; t < HPV_MAX_TERMS; ++t)
+#pragma unroll
         for (int f = 0; f < HPV_NFIELDS; ++f) {
             coef[t][f] = (t < a.n_terms) ? fmaf(eps, a.terms[t].a1[f], a.terms[t].a0[f]) : 0.0f;
             coef1[t][f] = (t < a.n_terms) ? a.terms[t].a1[f] : 0.0f;
@@ -358,13 +368,16 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
                 x = fmaf(a.el_geom[4 * e + 1], a.xi1[i], a.el_geom[4 * e + 0]);
                 if (DIM == 2) y = fmaf(a.el_geom[4 * e + 3], a.xi1[j], a.el_geom[4 * e + 2]);
             }
-            for (int t = 0; t < a.n_terms; ++t) gbar[t] = ba.Gbar[(size_t)t * ba.n_points + gp];
+#pragma unroll
+            for (int t = 0; t < HPV_MAX_TERMS; ++t)
+                if (t < a.n_terms) gbar[t] = ba.Gbar[(size_t)t * ba.n_points + gp];
         }
         // adjoints of the point fields (u, u_x, u_y, u_xx, u_yy)
         float gf[HPV_NFIELDS];
 #pragma unroll
         for (int k = 0; k < HPV_NFIELDS; ++k) gf[k] = 0.0f;
-        for (int t = 0; t < a.n_terms; ++t)
+#pragma unroll
+        for (int t = 0; t < HPV_MAX_TERMS; ++t)                        // absent terms: gbar = 0, coef = 0
 #pragma unroll
             for (int k = 0; k < HPV_NFIELDS; ++k) gf[k] = fmaf(gbar[t], coef[t][k], gf[k]);
         // directional mode: gx u_x + gy u_y = derivative of u along v = (gx, gy).  The tangent channel is seeded
@@ -383,23 +396,26 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
         int woff = hpv_off_wl(DIM, HP, 1);                           // constant-memory offsets: own induction variables
 #pragma unroll 1
         for (int l = 1; l <= top; ++l, woff += 2 * HP * HP + HP) {
-            hpv_activate<DIM, MX, MY, HP, ACT>(pre);                     // h_{l-1}
-            hpv_store_state<DIM, MX, MY, HP>(X, T, tid, pre);
+            hpv_to_mixed<DIM, MX, MY, HP, ACT>(pre);                     // mixed state of layer l-1
+            if (l >= 2) hpv_store_state<DIM, MX, MY, HP>(HPV_P(l - 1), 32, lane, pre);
+            hpv_activate<DIM, MX, MY, HP, ACT, true>(pre);               // h_{l-1}
+            hpv_store_state<DIM, MX, MY, HP>(X, 32, lane, pre);
             const float* W = s_th + woff;
-            hpv_matmul_slot<DIM, MX, MY, HP>(W, W + HP * HP, X, T, tid, pre);
-            if (l < top) hpv_store_state<DIM, MX, MY, HP>(HPV_P(l), T, tid, pre);
+            hpv_matmul_slot<DIM, MX, MY, HP>(W, W + HP * HP, X, 32, lane, pre);
         }
+        hpv_to_mixed<DIM, MX, MY, HP, ACT>(pre);                         // pre = mixed state of the top layer from here on
         {
-            State h = pre;                                             // pre = pre-activations of the top layer
-            hpv_activate<DIM, MX, MY, HP, ACT>(h);
-            hpv_store_state<DIM, MX, MY, HP>(X, T, tid, h);
+            State h = pre;
+            hpv_activate<DIM, MX, MY, HP, ACT, true>(h);
+            hpv_store_state<DIM, MX, MY, HP>(X, 32, lane, h);
         }
         // d loss / d eps needs the fields themselves; the directional mode is only chosen for forms without an
         // eps-dependent coefficient (hpv_form_directional), where this sum is identically 0
         if constexpr (!M::DIR) {
             float f[HPV_NFIELDS];
-            hpv_output_slot<DIM, MX, MY, HP>(Wo, X, T, tid, f);
-            for (int t = 0; t < a.n_terms; ++t) {
+            hpv_output_slot<DIM, MX, MY, HP>(Wo, X, 32, lane, f);
+#pragma unroll
+            for (int t = 0; t < HPV_MAX_TERMS; ++t) {
                 float d1 = 0.0f;
 #pragma unroll
                 for (int k = 0; k < HPV_NFIELDS; ++k) d1 = fmaf(coef1[t][k], f[k], d1);
@@ -408,11 +424,11 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
         }
 
         // ---- output layer: Wo/bo gradient (left factor h_top in X), adjoint of h_top ----
-        s_go[M::C_V * T + tid] = gf[0];
-        if constexpr (M::DX) s_go[M::C_DX * T + tid] = gf[1];
-        if constexpr (M::DY) s_go[M::C_DY * T + tid] = gf[2];
-        if constexpr (M::EX) s_go[M::C_EX * T + tid] = gf[3];
-        if constexpr (M::EY) s_go[M::C_EY * T + tid] = gf[4];
+        s_go[M::C_V * 32 + lane] = gf[0];
+        if constexpr (M::DX) s_go[M::C_DX * 32 + lane] = gf[1];
+        if constexpr (M::DY) s_go[M::C_DY * 32 + lane] = gf[2];
+        if constexpr (M::EX) s_go[M::C_EX * 32 + lane] = gf[3];
+        if constexpr (M::EY) s_go[M::C_EY * 32 + lane] = gf[4];
 #pragma unroll
         for (int m = 0; m < HP / 2; ++m) {
             const hpv_pair w = hpv_ld_pair(Wo + 2 * m);
@@ -430,43 +446,42 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
         int woff_t = a.off_wo - HP * HP;                             // = hpv_off_wt(DIM, HP, top)
 #pragma unroll 1
         for (int l = top; l >= 1; --l, woff_t -= 2 * HP * HP + HP) {
-            hpv_activate_bwd<DIM, MX, MY, HP, ACT>(pre, g);             // g := adjoint of the pre-activations of layer l
-            hpv_store_state<DIM, MX, MY, HP>(X, T, tid, g);
+            hpv_activate_bwd<DIM, MX, MY, HP, ACT, true>(pre, g);       // g := adjoint of the pre-activations of layer l
+            hpv_store_state<DIM, MX, MY, HP>(X, 32, lane, g);
             float* INl = (l - 1 >= 1) ? HPV_P(l - 1) : H0;
-            if (l - 1 >= 1) hpv_load_state<DIM, MX, MY, HP>(INl, T, tid, pre);
-            else HPV_LAYER1(pre);
+            if (l - 1 >= 1) hpv_load_state<DIM, MX, MY, HP>(INl, 32, lane, pre);   // mixed state of layer l-1
+            else { HPV_LAYER1(pre); hpv_to_mixed<DIM, MX, MY, HP, ACT>(pre); }
             {
                 State h = pre;
-                hpv_activate<DIM, MX, MY, HP, ACT>(h);                  // h_{l-1}: left factor of the W_l gradient
-                hpv_store_state<DIM, MX, MY, HP>(INl, T, tid, h);
+                hpv_activate<DIM, MX, MY, HP, ACT, true>(h);            // h_{l-1}: left factor of the W_l gradient
+                hpv_store_state<DIM, MX, MY, HP>(INl, 32, lane, h);
             }
             hpv_syncwarp(c);
             float* gW = s_gw + hpv_gw_wl(DIM, HP, l);
             hpv_wgrad_warp<SP, SP, M::NCH, HP, HP / 4, 4, true, 0, HP, DIM>(c, INl, X, gW, gW + HP * HP, s_cst);
             hpv_syncwarp(c);
             // adjoint of h_{l-1} = ADJ_l . W_l^T: the forward product loop on the transposed copy, inputs from X
-            hpv_matmul_slot<DIM, MX, MY, HP, false>(s_th + woff_t, nullptr, X, T, tid, g);
+            hpv_matmul_slot<DIM, MX, MY, HP, false>(s_th + woff_t, nullptr, X, 32, lane, g);
         }
 
         // ---- first layer ----
-        hpv_activate_bwd<DIM, MX, MY, HP, ACT>(pre, g);
-        hpv_store_state<DIM, MX, MY, HP>(X, T, tid, g);
+        hpv_activate_bwd<DIM, MX, MY, HP, ACT, true>(pre, g);
+        hpv_store_state<DIM, MX, MY, HP>(X, 32, lane, g);
         {
             HpvF4 o;
-            o.x = x; o.y = y; o.z = 1.0f; o.w = 0.0f; hpv_st4(s_in0 + (0 * T + tid) * 4, o);
+            o.x = x; o.y = y; o.z = 1.0f; o.w = 0.0f; hpv_st4(s_in0 + (0 * 32 + lane) * 4, o);
             if constexpr (M::DIR) {                    // the tangent seed is v . W1: its left factor is v
-                o.x = vx; o.y = vy; o.z = 0.0f; o.w = 0.0f; hpv_st4(s_in0 + (1 * T + tid) * 4, o);
+                o.x = vx; o.y = vy; o.z = 0.0f; o.w = 0.0f; hpv_st4(s_in0 + (1 * 32 + lane) * 4, o);
             } else {
-                if constexpr (M::DX) { o.x = 1.0f; o.y = 0.0f; o.z = 0.0f; o.w = 0.0f; hpv_st4(s_in0 + (M::C_DX * T + tid) * 4, o); }
-                if constexpr (M::DY) { o.x = 0.0f; o.y = 1.0f; o.z = 0.0f; o.w = 0.0f; hpv_st4(s_in0 + (M::C_DY * T + tid) * 4, o); }
+                if constexpr (M::DX) { o.x = 1.0f; o.y = 0.0f; o.z = 0.0f; o.w = 0.0f; hpv_st4(s_in0 + (M::C_DX * 32 + lane) * 4, o); }
+                if constexpr (M::DY) { o.x = 0.0f; o.y = 1.0f; o.z = 0.0f; o.w = 0.0f; hpv_st4(s_in0 + (M::C_DY * 32 + lane) * 4, o); }
             }
         }
         hpv_syncwarp(c);
         // channels that feed W1: value (x, y, 1), d/dx (1, 0, 0), d/dy (0, 1, 0); second-derivative seeds are 0.
         // The IN rows are ordered v, dx, dy, which is also the order of the stored channels (C_V, C_DX, C_DY).
         {
-            constexpr int nch1 = HpvBwdSmem<DIM, MX, MY, HP>::NCH1;
-            hpv_wgrad_warp<4, SP, nch1, 4, HP / 4, 4, false, 2, HP, DIM>(c, s_in0, X, s_gw, s_gw + DIM * HP, s_cst);
+            hpv_wgrad_warp<4, SP, NCH1, 4, HP / 4, 4, false, 2, HP, DIM>(c, s_in0, X, s_gw, s_gw + DIM * HP, s_cst);
             hpv_syncwarp(c);
         }
 #undef HPV_LAYER1

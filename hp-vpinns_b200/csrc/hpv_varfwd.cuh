@@ -76,8 +76,10 @@ HPV_HD void hpv_varfwd_body(const HpvCta& c, const HpvVarArgs& a) {
 
     for (int i = tid; i < Q; i += T) s_xi1[i] = a.xi1[i];
     const float eps = a.eps[0];
-    float coef[HPV_MAX_TERMS][HPV_NFIELDS];
+    float coef[HPV_MAX_TERMS][HPV_NFIELDS];              // registers: every loop over them is unrolled
+#pragma unroll
     for (int t = 0; t < HPV_MAX_TERMS; ++t)
+#pragma unroll
         for (int f = 0; f < HPV_NFIELDS; ++f)
             coef[t][f] = (t < a.n_terms) ? fmaf(eps, a.terms[t].a1[f], a.terms[t].a0[f]) : 0.0f;
     hpv_sync(c);
@@ -125,12 +127,16 @@ HPV_HD void hpv_varfwd_body(const HpvCta& c, const HpvVarArgs& a) {
                         s_G[t * L.GS + (p - base)] = a.field_in[((size_t)t * a.n_el + e) * npts_el + p];
                 } else {
                     float f[HPV_NFIELDS];
-                    hpv_net_point_slot<DIM, MX, MY, HP, ACT>(th, a.nhid, a.off_wo, x, y, s_slot, T, tid, f);
-                    for (int t = 0; t < a.n_terms; ++t) {
+                    // the slot rows are private to a thread; laid out per warp so that the strides are immediates
+                    hpv_net_point_slot<DIM, MX, MY, HP, ACT>(th, a.nhid, a.off_wo, x, y,
+                                                             s_slot + (tid >> 5) * (HpvMode<DIM, MX, MY>::NCH * 32 * HpvSP<HP>::value),
+                                                             32, tid & 31, f);
+#pragma unroll
+                    for (int t = 0; t < HPV_MAX_TERMS; ++t) {
                         float g = 0.0f;
 #pragma unroll
                         for (int k = 0; k < HPV_NFIELDS; ++k) g = fmaf(coef[t][k], f[k], g);
-                        s_G[t * L.GS + (p - base)] = g;
+                        if (t < a.n_terms) s_G[t * L.GS + (p - base)] = g;
                     }
                 }
             }

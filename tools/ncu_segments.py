@@ -18,7 +18,7 @@ for r in rows[hi + 1:]:
     if cur['first'] is None: cur['first'] = r[ai] if ai is not None else ''
     cur['n'] += n; cur['s'] += s; cur['ops'][op] += n; cur['sops'][op] += s; cur['lines'] += 1
     tot += n; ts += s
-    if op == 'BAR':
+    if op in ('BAR', 'WARPSYNC'):
         segs.append(cur); cur = dict(n=0, s=0, ops=collections.Counter(), first=None, lines=0, sops=collections.Counter())
 segs.append(cur)
 print("total instr %d samples %d" % (tot, ts))
