@@ -289,10 +289,12 @@ def run_ours(args):
     red = reduce_tensor(eng) if world > 1 else None
 
     def step():
-        eng.loss_and_grad()
-        if world > 1:
+        if world == 1:
+            eng.train_steps(1, want_history=False)      # forward, adjoint projection, reverse sweep, reduction + Adam
+        else:
+            eng.loss_and_grad()
             dist.all_reduce(red)
-        eng.adam_step()
+            eng.adam_step()
 
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
 

@@ -57,7 +57,9 @@ struct hpv_ctx {
     // parameters / optimiser
     DevBuf<float> theta_pad, eps;
     DevBuf<double> master, adam_m, adam_v, grad_out;
-    DevBuf<int> pad_index, pad_index2, step;
+    DevBuf<int> pad_index, pad_index2, ref_index;
+    DevBuf<double> adam_clock;         // two buffers of {beta1^t, beta2^t, t}; the update reads [adam_parity], writes the other
+    int adam_parity = 0;
     // quadrature / tables
     DevBuf<float> xi1, tab[HPV_NTAB], tabN[HPV_NTAB];
     // elements
@@ -316,11 +318,11 @@ int launch_mlpbwd_var(hpv_ctx* c) {
 }
 
 // `la` non-null: the launch also assembles the loss values (one extra CTA), see hpv_gradreduce_kernel.
-int launch_gradreduce(hpv_ctx* c, int n_parts, int accumulate, const HpvLossArgs* la = nullptr) {
+int launch_gradreduce(hpv_ctx* c, int n_parts, int accumulate, const HpvLossArgs* la = nullptr, const HpvAdamArgs* adam = nullptr) {
     HpvGradReduceArgs g;
     g.grad_part = c->grad_part.p; g.n_parts = n_parts; g.stride = c->grad_stride; g.n = c->net.theta_pad_n + 1;
     g.grad_pad = c->redbuf.p; g.accumulate = accumulate;
-    HPV_CK(hpv_launch_gradreduce(g, la, c->stream));
+    HPV_CK(hpv_launch_gradreduce(g, la, adam, c->stream));
     c->launches += 1;
     return HPV_OK;
 }
@@ -438,7 +440,7 @@ void hpv_destroy(hpv_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->theta_pad.release(); c->eps.release(); c->master.release(); c->adam_m.release(); c->adam_v.release();
-    c->grad_out.release(); c->pad_index.release(); c->pad_index2.release(); c->step.release(); c->xi1.release();
+    c->grad_out.release(); c->pad_index.release(); c->pad_index2.release(); c->ref_index.release(); c->adam_clock.release(); c->xi1.release();
     for (int t = 0; t < HPV_NTAB; ++t) { c->tab[t].release(); c->tabN[t].release(); }
     c->geom.release(); c->F.release(); c->Res.release(); c->el_loss.release(); c->Upart.release(); c->Gbar.release();
     c->ntest.release(); c->cta_tile_begin.release(); c->el_first_cta.release(); c->el_part_off.release();
@@ -490,9 +492,15 @@ int hpv_set_network(hpv_ctx* c, int dim, const int* layers, int n_layers, int ac
     HPV_CK(c->master.alloc(P + 1)); HPV_CK(c->adam_m.alloc(P + 1)); HPV_CK(c->adam_v.alloc(P + 1));
     HPV_CK(c->grad_out.alloc(P + 1));
     HPV_CK(cudaMemsetAsync(c->master.p, 0, (P + 1) * sizeof(double), c->stream));
-    HPV_CK(c->step.alloc(1));
+    HPV_CK(c->adam_clock.alloc(6));
     { int r = upload(c, c->pad_index, net.pad_index); if (r) return r; }
     { int r = upload(c, c->pad_index2, net.pad_index2); if (r) return r; }
+    {
+        std::vector<int> ref(net.theta_pad_n + 1, -1);           // padded index -> reference-order index
+        for (int i = 0; i < P; ++i) ref[net.pad_index[i]] = i;
+        ref[net.theta_pad_n] = P;                                 // the eps slot of the reduce buffer
+        int r = upload(c, c->ref_index, ref); if (r) return r;
+    }
     for (int s = 0; s < HPV_MAX_POINT_SETS; ++s) c->ps[s].active = false;
     return hpv_reset_optimizer(c);
 }
@@ -672,14 +680,17 @@ int hpv_forward_async(hpv_ctx* c) {
     return launch_forward(c);
 }
 
-static int unpad_grad(hpv_ctx* c, int update) {
-    HpvAdamArgs a; memset(&a, 0, sizeof(a));
+// Arguments of the Adam / un-padding kernels.  With update != 0 the caller must call adam_launched() after the launch.
+static void fill_adam_args(hpv_ctx* c, HpvAdamArgs& a, int update, bool wrote[3]) {
+    memset(&a, 0, sizeof(a));
     a.grad_pad = c->redbuf.p; a.pad_index = c->pad_index.p; a.pad_index2 = c->pad_index2.p; a.n_theta = c->net.n_theta; a.theta_pad_n = c->net.theta_pad_n;
+    a.ref_index = c->ref_index.p;
     a.theta = c->master.p; a.m = c->adam_m.p; a.v = c->adam_v.p; a.theta_pad = c->theta_pad.p; a.eps = c->eps.p;
     a.grad_out = c->grad_out.p; a.train_eps = c->train_eps;
-    a.lr = (float)c->lr; a.b1 = (float)c->b1; a.b2 = (float)c->b2; a.eps_hat = (float)c->eps_hat;
-    a.step = c->step.p; a.update = update;
-    bool wrote[3] = {false, false, false};
+    a.lr = c->lr; a.b1 = c->b1; a.b2 = c->b2; a.eps_hat = c->eps_hat;
+    a.st_in = c->adam_clock.p + 3 * c->adam_parity; a.st_out = c->adam_clock.p + 3 * (c->adam_parity ^ 1);
+    a.update = update;
+    wrote[0] = wrote[1] = wrote[2] = false;
     if (update && c->adam_direct) {
         // mirrors this context owns right now take the update in place; a mirror that was already stale stays stale
         std::lock_guard<std::mutex> lock(g_owner_mutex);
@@ -687,10 +698,20 @@ static int unpad_grad(hpv_ctx* c, int update) {
         for (int k = 0; k < 3; ++k)
             if (c->mirror[k] && g_owner[c->device & 15][hpi][k] == c) { a.mirror[k] = c->mirror[k]; wrote[k] = true; }
     }
+}
+
+static void adam_launched(hpv_ctx* c, const bool wrote[3]) {
+    c->adam_parity ^= 1;
+    for (int k = 0; k < 3; ++k) if (!wrote[k]) c->mirror_stale[k] = true;
+}
+
+static int unpad_grad(hpv_ctx* c, int update) {
+    HpvAdamArgs a;
+    bool wrote[3];
+    fill_adam_args(c, a, update, wrote);
     HPV_CK(hpv_launch_adam(a, c->stream));
     c->launches += 1;
-    if (update)
-        for (int k = 0; k < 3; ++k) if (!wrote[k]) c->mirror_stale[k] = true;
+    if (update) adam_launched(c, wrote);
     return HPV_OK;
 }
 
@@ -806,7 +827,8 @@ int hpv_configure_training(hpv_ctx* c, double wv, unsigned mask, int train_eps, 
     return HPV_OK;
 }
 
-int hpv_loss_and_grad(hpv_ctx* c) {
+// fuse_adam: the step's last gradient reduction also applies the Adam update (single-GPU training step).
+static int loss_and_grad_impl(hpv_ctx* c, bool fuse_adam) {
     { int r = need_net(c); if (r) return r; }
     HPV_CK(cudaSetDevice(c->device));
     const bool use_v = c->wv != 0.0;
@@ -835,16 +857,28 @@ int hpv_loss_and_grad(hpv_ctx* c) {
         la.blk[s] = ps.blk_loss.p; la.nblk[s] = ps.n_ctas;
     }
     if (pending >= 0) {
-        int r = launch_gradreduce(c, pending, acc, &la);
-        if (r) return r;
+        if (fuse_adam) {
+            HpvAdamArgs ad;
+            bool wrote[3];
+            fill_adam_args(c, ad, 1, wrote);
+            int r = launch_gradreduce(c, pending, acc, &la, &ad);
+            if (r) return r;
+            adam_launched(c, wrote);
+        } else {
+            int r = launch_gradreduce(c, pending, acc, &la);
+            if (r) return r;
+        }
     } else {
         HPV_CK(cudaMemsetAsync(c->redbuf.p, 0, c->loss_off * sizeof(float), c->stream));
         hpv_losses_kernel<<<1, 32, 0, c->stream>>>(la);
         HPV_CK(cudaGetLastError());
         c->launches += 1;
+        if (fuse_adam) return unpad_grad(c, 1);
     }
     return HPV_OK;
 }
+
+int hpv_loss_and_grad(hpv_ctx* c) { return loss_and_grad_impl(c, false); }
 
 int hpv_reduce_buffer(hpv_ctx* c, void** p, int* n) {
     if (!c || !p || !n) return HPV_ERR_ARG;
@@ -885,7 +919,10 @@ int hpv_reset_optimizer(hpv_ctx* c) {
     const int P = c->net.n_theta;
     HPV_CK(cudaMemsetAsync(c->adam_m.p, 0, (P + 1) * sizeof(double), c->stream));
     HPV_CK(cudaMemsetAsync(c->adam_v.p, 0, (P + 1) * sizeof(double), c->stream));
-    HPV_CK(cudaMemsetAsync(c->step.p, 0, sizeof(int), c->stream));
+    const double clock0[6] = {1.0, 1.0, 0.0, 1.0, 1.0, 0.0};
+    HPV_CK(cudaMemcpyAsync(c->adam_clock.p, clock0, sizeof(clock0), cudaMemcpyHostToDevice, c->stream));
+    HPV_CK(cudaStreamSynchronize(c->stream));                     // clock0 is on the stack
+    c->adam_parity = 0;
     return HPV_OK;
 }
 
@@ -895,10 +932,10 @@ int hpv_train_steps(hpv_ctx* c, int nsteps, double* hist) {
     DevBuf<float> dh;
     if (hist && nsteps) HPV_CK(dh.alloc((size_t)nsteps * 6));
     for (int it = 0; it < nsteps; ++it) {
-        int r = hpv_loss_and_grad(c);
-        if (!r && hist)
+        // one launch sequence per step: forward, adjoint projection, reverse sweep, reduction + losses + Adam
+        int r = loss_and_grad_impl(c, true);
+        if (!r && hist)       // the loss values are those of the parameters the gradient was taken at
             HPV_CK(cudaMemcpyAsync(dh.p + (size_t)it * 6, c->redbuf.p + c->loss_off, 6 * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
-        if (!r) r = hpv_adam_step(c);
         if (r) { dh.release(); return r; }
     }
     if (hist && nsteps) {

@@ -26,9 +26,47 @@ cudaError_t hpv_launch_adjproj(const HpvAdjArgs& a, int grid, size_t smem, cudaS
     return cudaGetLastError();
 }
 
-// CTAs 0 .. nred-1 reduce 32 gradient entries each; with has_loss the last CTA assembles the loss values.
-__global__ void __launch_bounds__(256) hpv_gradreduce_kernel(const HpvGradReduceArgs a, const HpvLossArgs la, int nred) {
-    __shared__ __align__(16) unsigned char smem[8 * 32 * 4];
+// TF1 Adam for one parameter (reference order index r; r == n_theta: eps):
+//   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  lr_t = lr sqrt(1-b2^t)/(1-b1^t);  theta -= lr_t m/(sqrt(v)+eps_hat)
+// (eps_hat outside the bias correction, as tf.train.AdamOptimizer) in float64 master copies; refreshes the fp32
+// padded parameters the kernels read -- in global memory and in the constant-memory mirrors this context owns
+// (the constant caches are invalidated at the next launch, so the following kernels see the update).
+__device__ __forceinline__ void hpv_adam_one(const HpvAdamArgs& a, int r, double g, double lr_t) {
+    if (a.grad_out) a.grad_out[r] = g;
+    if (!a.update) return;
+    const bool is_eps = (r == a.n_theta);
+    if (is_eps && !a.train_eps) return;
+    const double b1 = a.b1, b2 = a.b2;
+    const double m = b1 * a.m[r] + (1.0 - b1) * g;
+    const double v = b2 * a.v[r] + (1.0 - b2) * g * g;
+    const double th = a.theta[r] - lr_t * m / (sqrt(v) + (double)a.eps_hat);
+    a.m[r] = m; a.v[r] = v; a.theta[r] = th;
+    if (is_eps) { a.eps[0] = (float)th; return; }
+    const int i1 = a.pad_index[r], i2 = a.pad_index2[r];
+    const float tf = (float)th;
+    a.theta_pad[i1] = tf;
+    if (i2 >= 0) a.theta_pad[i2] = tf;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float* mk = a.mirror[k];
+        if (mk) { mk[i1] = tf; if (i2 >= 0) mk[i2] = tf; }
+    }
+}
+
+// The optimizer clock {b1^t, b2^t, t} is read from st_in by everybody and advanced into st_out (the host swaps the
+// two buffers between updates) by one thread of the launch: no ordering between CTAs is needed.
+__device__ __forceinline__ double hpv_adam_clock(const HpvAdamArgs& a, bool writer) {
+    if (!a.update) return 0.0;
+    const double p1 = a.st_in[0] * (double)a.b1, p2 = a.st_in[1] * (double)a.b2;
+    if (writer) { a.st_out[0] = p1; a.st_out[1] = p2; a.st_out[2] = a.st_in[2] + 1.0; }
+    return (double)a.lr * sqrt(1.0 - p2) / (1.0 - p1);
+}
+
+// CTAs 0 .. nred-1 reduce 32 gradient entries each (and, with has_adam, update the parameters those entries
+// belong to); with has_loss the last CTA assembles the loss values.
+__global__ void __launch_bounds__(1024) hpv_gradreduce_kernel(const HpvGradReduceArgs a, const HpvLossArgs la, int nred,
+                                                              const HpvAdamArgs ad, int has_adam) {
+    __shared__ __align__(16) unsigned char smem[32 * 32 * 4];
     if ((int)blockIdx.x >= nred) {
         if (threadIdx.x < 32) hpv_losses_warp(la, threadIdx.x);
         return;
@@ -36,54 +74,37 @@ __global__ void __launch_bounds__(256) hpv_gradreduce_kernel(const HpvGradReduce
     HpvCta c;
     c.tid = threadIdx.x; c.nthreads = blockDim.x; c.bid = blockIdx.x; c.nblocks = nred;
     c.smem = smem; c.emu = nullptr;
-    hpv_gradreduce_body(c, a);
+    const float g = hpv_gradreduce_body(c, a);
+    if (has_adam && threadIdx.x < 32) {
+        const int i = blockIdx.x * 32 + threadIdx.x;
+        const double lr_t = hpv_adam_clock(ad, i == 0);
+        if (i < a.n) {
+            const int r = ad.ref_index[i];
+            if (r >= 0) hpv_adam_one(ad, r, (double)g, lr_t);
+        }
+    }
 }
 
-cudaError_t hpv_launch_gradreduce(const HpvGradReduceArgs& a, const HpvLossArgs* la, cudaStream_t s) {
+cudaError_t hpv_launch_gradreduce(const HpvGradReduceArgs& a, const HpvLossArgs* la, const HpvAdamArgs* adam, cudaStream_t s) {
     const int nred = (a.n + 31) / 32;
     HpvLossArgs l0;
     memset(&l0, 0, sizeof(l0));
-    hpv_gradreduce_kernel<<<nred + (la ? 1 : 0), 256, 0, s>>>(a, la ? *la : l0, nred);
+    HpvAdamArgs a0;
+    memset(&a0, 0, sizeof(a0));
+    // 32 groups of partials per CTA when there are many of them (the sum is latency-bound otherwise)
+    const int block = a.n_parts >= 128 ? 1024 : 256;
+    hpv_gradreduce_kernel<<<nred + (la ? 1 : 0), block, 0, s>>>(a, la ? *la : l0, nred, adam ? *adam : a0, adam ? 1 : 0);
     return cudaGetLastError();
 }
 
-// One CTA; thread-strided over the parameters (reference order, eps last).  Always un-pads the gradient; with
-// update != 0 applies
-//   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  lr_t = lr sqrt(1-b2^t)/(1-b1^t);  theta -= lr_t m/(sqrt(v)+eps_hat)
-// (eps_hat outside the bias correction, as in TF1) in float64 master copies, refreshes the fp32 padded
-// parameters the kernels read -- in global memory and in the constant-memory mirrors this context owns (the
-// constant caches are invalidated at the next launch, so the following kernels see the update) -- and advances
-// the step counter (single CTA: every thread has read t before thread 0 stores t + 1).
+// Stand-alone form (after the NCCL all-reduce of the multi-GPU step, and to un-pad a gradient for the host):
+// one CTA, thread-strided over the parameters (reference order, eps last).
 __global__ void __launch_bounds__(1024) hpv_adam_kernel(const HpvAdamArgs a) {
-    const HpvAdamArgs& d = a;
-    const int t = a.update ? a.step[0] + 1 : 0;
-    const double b1 = a.b1, b2 = a.b2;
-    const double lr_t = a.update ? (double)a.lr * sqrt(1.0 - pow(b2, (double)t)) / (1.0 - pow(b1, (double)t)) : 0.0;
-    __syncthreads();
-    for (int i = threadIdx.x; i <= a.n_theta; i += blockDim.x) {
-        const bool is_eps = (i == a.n_theta);
-        const double g = (double)(is_eps ? a.grad_pad[a.theta_pad_n] : a.grad_pad[a.pad_index[i]]);
-        if (d.grad_out) d.grad_out[i] = g;
-        if (!a.update) continue;
-        if (is_eps && !a.train_eps) continue;
-        const double m = b1 * d.m[i] + (1.0 - b1) * g;
-        const double v = b2 * d.v[i] + (1.0 - b2) * g * g;
-        const double th = d.theta[i] - lr_t * m / (sqrt(v) + (double)a.eps_hat);
-        d.m[i] = m; d.v[i] = v; d.theta[i] = th;
-        if (is_eps) a.eps[0] = (float)th;
-        else {
-            const int i1 = a.pad_index[i], i2 = a.pad_index2[i];
-            const float tf = (float)th;
-            a.theta_pad[i1] = tf;
-            if (i2 >= 0) a.theta_pad[i2] = tf;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                float* mk = a.mirror[k];
-                if (mk) { mk[i1] = tf; if (i2 >= 0) mk[i2] = tf; }
-            }
-        }
+    const double lr_t = hpv_adam_clock(a, threadIdx.x == 0);
+    for (int r = threadIdx.x; r <= a.n_theta; r += blockDim.x) {
+        const double g = (double)(r == a.n_theta ? a.grad_pad[a.theta_pad_n] : a.grad_pad[a.pad_index[r]]);
+        hpv_adam_one(a, r, g, lr_t);
     }
-    if (a.update && threadIdx.x == 0) a.step[0] = t;
 }
 
 cudaError_t hpv_launch_adam(const HpvAdamArgs& a, cudaStream_t s) {

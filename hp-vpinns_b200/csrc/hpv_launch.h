@@ -75,8 +75,9 @@ __device__ inline void hpv_losses_warp(const HpvLossArgs& a, int lane) {
     }
 }
 #endif
-// la non-null: one extra CTA assembles the loss values in the same launch
-cudaError_t hpv_launch_gradreduce(const HpvGradReduceArgs& a, const HpvLossArgs* la, cudaStream_t s);
+// la non-null: one extra CTA assembles the loss values in the same launch.  adam non-null (single-GPU training
+// step): every reduced gradient entry is consumed by the Adam update of its parameter in the same launch.
+cudaError_t hpv_launch_gradreduce(const HpvGradReduceArgs& a, const HpvLossArgs* la, const struct HpvAdamArgs* adam, cudaStream_t s);
 struct HpvAdamArgs {
     const float* grad_pad;     // padded gradient (+ d eps at index theta_pad_n)
     const int* pad_index;      // [n_theta] reference-order index -> padded index
@@ -90,8 +91,12 @@ struct HpvAdamArgs {
     float* eps;                // device scalar read by the kernels
     double* grad_out;          // [n_theta + 1] unpadded gradient or null
     int train_eps;
-    float lr, b1, b2, eps_hat;
-    int* step;                 // device step counter (the update uses t = step + 1 and stores it back)
+    double lr, b1, b2, eps_hat;
+    const int* ref_index;      // [theta_pad_n + 1] padded index -> reference-order index (eps: n_theta), -1: none
+    // optimizer clock, double-buffered by the host (st_in = the other buffer of st_out): {beta1^t, beta2^t, t}.
+    // The powers are running products, as TF1 keeps them (beta1_power, beta2_power variables).
+    const double* st_in;
+    double* st_out;
     int update;                // 0: only unpad the gradient, 1: also apply the Adam update
 };
 cudaError_t hpv_launch_adam(const HpvAdamArgs& a, cudaStream_t s);

@@ -502,8 +502,10 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
     if (tid == 0) gpart[a.theta_pad_n] = dtot;
 }
 
-// K3: grad_pad[i] (+)= sum over CTAs of grad_part[c][i], fixed order.  One CTA of 256 threads = 32 entries x 8
-// CTA-groups.  accumulate != 0 adds onto the existing value (several losses into one gradient).
+// K3: grad_pad[i] (+)= sum over CTAs of grad_part[c][i], fixed order.  One CTA = 32 entries x (nthreads / 32)
+// groups of partials; a thread sums every ngrp-th partial with four independent accumulators (loads in flight),
+// the groups are combined in a fixed order.  accumulate != 0 adds onto the existing value (several losses into
+// one gradient).  Returns the reduced value to the threads of group 0 (others: 0).
 struct HpvGradReduceArgs {
     const float* grad_part;
     int n_parts, stride, n;    // n entries (theta_pad_n + 1)
@@ -511,18 +513,29 @@ struct HpvGradReduceArgs {
     int accumulate;
 };
 
-HPV_HD void hpv_gradreduce_body(const HpvCta& c, const HpvGradReduceArgs& a) {
-    float* s = reinterpret_cast<float*>(c.smem);     // [8][32]
+HPV_HD float hpv_gradreduce_body(const HpvCta& c, const HpvGradReduceArgs& a) {
+    float* s = reinterpret_cast<float*>(c.smem);     // [ngrp][32]
     const int li = c.tid & 31, grp = c.tid >> 5, ngrp = c.nthreads >> 5;
     const int i = c.bid * 32 + li;
-    float acc = 0.0f;
-    if (i < a.n)
-        for (int p = grp; p < a.n_parts; p += ngrp) acc += a.grad_part[(size_t)p * a.stride + i];
-    s[grp * 32 + li] = acc;
-    hpv_sync(c);
-    if (grp == 0 && i < a.n) {
-        float t = 0.0f;
-        for (int g2 = 0; g2 < ngrp; ++g2) t += s[g2 * 32 + li];
-        a.grad_pad[i] = a.accumulate ? a.grad_pad[i] + t : t;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    if (i < a.n) {
+        const float* src = a.grad_part + i;
+        int p = grp;
+        for (; p + 3 * ngrp < a.n_parts; p += 4 * ngrp) {
+            a0 += src[(size_t)p * a.stride];
+            a1 += src[(size_t)(p + ngrp) * a.stride];
+            a2 += src[(size_t)(p + 2 * ngrp) * a.stride];
+            a3 += src[(size_t)(p + 3 * ngrp) * a.stride];
+        }
+        for (; p < a.n_parts; p += ngrp) a0 += src[(size_t)p * a.stride];
     }
+    s[grp * 32 + li] = (a0 + a1) + (a2 + a3);
+    hpv_sync(c);
+    float t = 0.0f;
+    if (grp == 0 && i < a.n) {
+        for (int g2 = 0; g2 < ngrp; ++g2) t += s[g2 * 32 + li];
+        if (a.accumulate) t += a.grad_pad[i];
+        a.grad_pad[i] = t;
+    }
+    return t;
 }

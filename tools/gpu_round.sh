@@ -2,14 +2,16 @@
 # One GPU-box visit: parity tests, bench (default + A/B variants), ncu launch list and full captures.
 # Usage (from the repo root, under gpurun): bash tools/gpu_round.sh TAG
 TAG=${1:-rXX}
+VARIANTS=${2:-}
 O=gpurun_out/$TAG
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $O/gpu.txt 2>&1
 echo "== pytest -m gpu" ; timeout 900 python -m pytest tests -m gpu -q > $O/pytest_gpu.log 2>&1; echo "pytest exit $?" | tee -a $O/pytest_gpu.log; tail -5 $O/pytest_gpu.log
 echo "== bench default"; timeout 600 python bench.py > $O/bench_default.json 2> $O/bench_default.err; tail -c 3000 $O/bench_default.json
 echo "== bench two-tangent sweep"; HPV_BWD_DIR=0 timeout 300 python bench.py --steps 500 --no-cpu-baseline > $O/bench_dir0.json 2> $O/bench_dir0.err
-echo "== bench, Adam with re-staging copies"; HPV_ADAM_DIRECT=0 timeout 300 python bench.py --steps 500 --no-cpu-baseline > $O/bench_adam0.json 2> $O/bench_adam0.err
-echo "== bench DIR block 64"; HPV_BWD_BLOCK=64 timeout 300 python bench.py --steps 500 --no-cpu-baseline > $O/bench_blk64.json 2> $O/bench_blk64.err
+for v in $VARIANTS; do
+  echo "== bench variant lib $v"; HPV_LIB=$PWD/hp-vpinns_b200/libhpv_$v.so timeout 300 python bench.py --steps 500 --no-cpu-baseline > $O/bench_$v.json 2> $O/bench_$v.err
+done
 echo "== bench c4 on one GPU"; timeout 300 python bench.py --workload c4 --steps 100 --no-cpu-baseline > $O/bench_c4.json 2> $O/bench_c4.err
 python - <<PY
 import json,glob

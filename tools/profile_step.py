@@ -10,7 +10,6 @@ a = ap.parse_args()
 wl = bench.build_workload(a.workload)
 eng = bench.make_engine(wl, 0)
 for _ in range(a.steps):
-    eng.loss_and_grad()
-    eng.adam_step()
+    eng.train_steps(1, want_history=False)
 eng.sync()
 print("losses", eng.read_losses()[:2], "launches", eng.launch_count())
