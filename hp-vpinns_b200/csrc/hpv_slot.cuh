@@ -93,16 +93,21 @@ HPV_HD void hpv_matmul_slot(const float* W, const float* b, const float* slot, i
     static_assert(HP % 4 == 0, "padded hidden width must be a multiple of 4 (128-bit weight loads)");
     // two independent induction variables: the weight pointer (constant memory, must stay in uniform registers so
     // that the loads are LDCU and the FFMA2 take a UR operand) and the slot-row pointer (per-thread, vector)
+    // The inputs of trip i4 + 1 are fetched while trip i4 computes (the loop is rolled, so nothing else would hide
+    // the shared-memory latency at the top of each trip); the last trip re-reads its own inputs.
     const float* row = slot + (size_t)tid * SP;
     const float* wr0 = W;
+    HpvF4 xn[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) xn[c] = hpv_ld4(row + (size_t)c * T * SP);
 #pragma unroll 1
-    for (int i4 = 0; i4 < HP / 4; ++i4, row += 4, wr0 += 4 * HP) {
+    for (int i4 = 0; i4 < HP / 4; ++i4, wr0 += 4 * HP) {
         float x[NCH][4];
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            const HpvF4 v = hpv_ld4(row + (size_t)c * T * SP);
-            x[c][0] = v.x; x[c][1] = v.y; x[c][2] = v.z; x[c][3] = v.w;
-        }
+        for (int c = 0; c < NCH; ++c) { x[c][0] = xn[c].x; x[c][1] = xn[c].y; x[c][2] = xn[c].z; x[c][3] = xn[c].w; }
+        if (i4 + 1 < HP / 4) row += 4;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) xn[c] = hpv_ld4(row + (size_t)c * T * SP);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float* wr = wr0 + k * HP;
