@@ -285,12 +285,14 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     eng.set_stream(stream.cuda_stream)
-    from hpv_b200.distributed import reduce_tensor
+    from hpv_b200.distributed import reduce_tensor, connect_peers
     red = reduce_tensor(eng) if world > 1 else None
+    peer = world > 1 and args.collective == "peer" and connect_peers(eng)
 
     def step():
-        if world == 1:
-            eng.train_steps(1, want_history=False)      # forward, adjoint projection, reverse sweep, reduction + Adam
+        if world == 1 or peer:
+            # forward, adjoint projection, reverse sweep, reduction [+ peer-memory exchange over NVLink] + Adam
+            eng.train_steps(1, want_history=False)
         else:
             eng.loss_and_grad()
             dist.all_reduce(red)
@@ -423,7 +425,8 @@ def run_ours(args):
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if name == "c4" else "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl["desc"], "elements_total": n_el, "elements_per_gpu": wl["n_el_local"],
-                           "step": "fused forward (residuals + lossv) + backward (d theta) + %sAdam" % ("NCCL all-reduce + " if world > 1 else ""),
+                           "step": "fused forward (residuals + lossv) + backward (d theta) + %sAdam" % (
+                               ("peer-memory gradient exchange (in the reduction kernel) + " if peer else "NCCL all-reduce + ") if world > 1 else ""),
                            "parallelism": "elements block-partitioned over %d GPU(s)" % world,
                            "l2": "flushed between timed steps (256 MB fill, untimed)", "launch_geometry": info},
                 "clocks": clocks, "gpu_launches": int(launches),
@@ -447,6 +450,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "c3", "c4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="N>1: gradient sum inside the step's last kernel over peer memory (default) or NCCL all-reduce")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -41,6 +41,8 @@ SIGNATURES = {
     "hpv_loss_and_grad": (c_int, [c_void_p]),
     "hpv_reduce_buffer": (c_int, [c_void_p, ctypes.POINTER(c_void_p), P_int]),
     "hpv_adam_step": (c_int, [c_void_p]),
+    "hpv_peer_export": (c_int, [c_void_p, c_int, ctypes.c_char_p]),
+    "hpv_peer_connect": (c_int, [c_void_p, c_int, c_int, ctypes.c_char_p]),
     "hpv_read_losses": (c_int, [c_void_p, P_double, c_int]),
     "hpv_read_grad": (c_int, [c_void_p, P_double, c_int, P_double]),
     "hpv_reset_optimizer": (c_int, [c_void_p]),

@@ -58,6 +58,14 @@ struct hpv_ctx {
     DevBuf<float> theta_pad, eps;
     DevBuf<double> master, adam_m, adam_v, grad_out;
     DevBuf<int> pad_index, pad_index2, ref_index;
+    // gradient exchange over peer memory (hpv_peer_export / hpv_peer_connect)
+    DevBuf<float> peer_inbox_own;
+    DevBuf<unsigned> peer_flags_own, peer_err;
+    int peer_n = 0, peer_rank = 0, peer_nvp = 0, peer_nchunks = 0;
+    unsigned peer_seq = 0;
+    float* peer_inbox[HPV_MAX_PEERS] = {nullptr};
+    unsigned* peer_flags[HPV_MAX_PEERS] = {nullptr};
+    std::vector<void*> peer_opened;
     DevBuf<double> adam_clock;         // two buffers of {beta1^t, beta2^t, t}; the update reads [adam_parity], writes the other
     int adam_parity = 0;
     // quadrature / tables
@@ -277,9 +285,9 @@ int ensure_ready(hpv_ctx* c) {
     c->adj_grid = c->n_el * c->slabs_per_el;
     c->adj_smem = (size_t)hpv_adj_smem(a).total * 4;
     if (c->adj_smem > 227 * 1024) return fail(c, HPV_ERR_LIMIT, "adjoint projection shared-memory plan exceeds 227 KB");
-    c->loss_off = hpv_align4(c->net.theta_pad_n + 1);
-    HPV_CK(c->redbuf.alloc(c->loss_off + 8));
-    HPV_CK(cudaMemsetAsync(c->redbuf.p, 0, (c->loss_off + 8) * sizeof(float), c->stream));
+    c->loss_off = ((c->net.theta_pad_n + 1 + 31) / 32) * 32;       // the losses start a 32-entry chunk of their own
+    HPV_CK(c->redbuf.alloc(c->loss_off + 32));
+    HPV_CK(cudaMemsetAsync(c->redbuf.p, 0, (c->loss_off + 32) * sizeof(float), c->stream));
     c->ready = true;
     return HPV_OK;
 }
@@ -318,11 +326,19 @@ int launch_mlpbwd_var(hpv_ctx* c) {
 }
 
 // `la` non-null: the launch also assembles the loss values (one extra CTA), see hpv_gradreduce_kernel.
-int launch_gradreduce(hpv_ctx* c, int n_parts, int accumulate, const HpvLossArgs* la = nullptr, const HpvAdamArgs* adam = nullptr) {
+int launch_gradreduce(hpv_ctx* c, int n_parts, int accumulate, const HpvLossArgs* la = nullptr, const HpvAdamArgs* adam = nullptr,
+                      bool exchange = false) {
     HpvGradReduceArgs g;
     g.grad_part = c->grad_part.p; g.n_parts = n_parts; g.stride = c->grad_stride; g.n = c->net.theta_pad_n + 1;
     g.grad_pad = c->redbuf.p; g.accumulate = accumulate;
-    HPV_CK(hpv_launch_gradreduce(g, la, adam, c->stream));
+    HpvPeerArgs pa;
+    if (exchange) {
+        memset(&pa, 0, sizeof(pa));
+        pa.nranks = c->peer_n; pa.rank = c->peer_rank; pa.seq = ++c->peer_seq; pa.nvp = c->peer_nvp; pa.nchunks = c->peer_nchunks;
+        for (int r = 0; r < c->peer_n; ++r) { pa.inbox[r] = c->peer_inbox[r]; pa.flags[r] = c->peer_flags[r]; }
+        pa.err = c->peer_err.p; pa.timeout_ns = 5000000000ull;
+    }
+    HPV_CK(hpv_launch_gradreduce(g, la, adam, exchange ? &pa : nullptr, c->loss_off, c->stream));
     c->launches += 1;
     return HPV_OK;
 }
@@ -385,6 +401,15 @@ int launch_mlpbwd_points(hpv_ctx* c, PointSet& ps, int& grid_out) {
 
 // total = wv*lossv + point losses, for the case that no gradient reduction ran (nothing to fuse it into)
 __global__ void hpv_losses_kernel(const HpvLossArgs a) { hpv_losses_warp(a, threadIdx.x); }
+
+// After a synchronisation: did a wait of the peer exchange time out (a peer rank died or never launched)?
+int check_peer_error(hpv_ctx* c) {
+    if (!c->peer_n) return HPV_OK;
+    unsigned e = 0;
+    HPV_CK(cudaMemcpy(&e, c->peer_err.p, sizeof(e), cudaMemcpyDeviceToHost));
+    if (e) return fail(c, HPV_ERR_CUDA, "peer gradient exchange timed out (5 s): a rank of the node did not arrive");
+    return HPV_OK;
+}
 
 int need_net(hpv_ctx* c) {
     if (!c) return HPV_ERR_ARG;
@@ -449,6 +474,8 @@ void hpv_destroy(hpv_ctx* c) {
         c->ps[s].pts.release(); c->ps[s].target.release(); c->ps[s].resid.release(); c->ps[s].gbar.release();
         c->ps[s].blk_loss.release();
     }
+    for (void* q : c->peer_opened) cudaIpcCloseMemHandle(q);
+    c->peer_inbox_own.release(); c->peer_flags_own.release(); c->peer_err.release();
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     {
         std::lock_guard<std::mutex> lock(g_owner_mutex);
@@ -856,12 +883,18 @@ static int loss_and_grad_impl(hpv_ctx* c, bool fuse_adam) {
         pending = grid;
         la.blk[s] = ps.blk_loss.p; la.nblk[s] = ps.n_ctas;
     }
+    const bool exchange = fuse_adam && c->peer_n > 1;
+    if (exchange && pending < 0) {
+        // nothing selected on this rank: it still takes part in the exchange, with a zero vector
+        HPV_CK(cudaMemsetAsync(c->redbuf.p, 0, c->loss_off * sizeof(float), c->stream));
+        pending = 0; acc = 1;
+    }
     if (pending >= 0) {
         if (fuse_adam) {
             HpvAdamArgs ad;
             bool wrote[3];
             fill_adam_args(c, ad, 1, wrote);
-            int r = launch_gradreduce(c, pending, acc, &la, &ad);
+            int r = launch_gradreduce(c, pending, acc, &la, &ad, exchange);
             if (r) return r;
             adam_launched(c, wrote);
         } else {
@@ -888,6 +921,52 @@ int hpv_reduce_buffer(hpv_ctx* c, void** p, int* n) {
     return HPV_OK;
 }
 
+int hpv_peer_export(hpv_ctx* c, int nranks, unsigned char* handles) {
+    if (!c || !handles) return HPV_ERR_ARG;
+    if (nranks < 2 || nranks > HPV_MAX_PEERS) return fail(c, HPV_ERR_ARG, "peer exchange supports 2..8 ranks of one node");
+    HPV_CK(cudaSetDevice(c->device));
+    { int r = ensure_ready(c); if (r) return r; }
+    if (c->peer_n) return fail(c, HPV_ERR_STATE, "peer exchange is already connected");
+    c->peer_nchunks = c->loss_off / 32 + 1;
+    c->peer_nvp = c->peer_nchunks * 32;
+    HPV_CK(c->peer_inbox_own.alloc((size_t)2 * nranks * c->peer_nvp));
+    HPV_CK(c->peer_flags_own.alloc((size_t)2 * nranks * c->peer_nchunks));
+    HPV_CK(c->peer_err.alloc(1));
+    HPV_CK(cudaMemset(c->peer_inbox_own.p, 0, c->peer_inbox_own.n * sizeof(float)));
+    HPV_CK(cudaMemset(c->peer_flags_own.p, 0, c->peer_flags_own.n * sizeof(unsigned)));
+    HPV_CK(cudaMemset(c->peer_err.p, 0, sizeof(unsigned)));
+    cudaIpcMemHandle_t h0, h1;
+    HPV_CK(cudaIpcGetMemHandle(&h0, c->peer_inbox_own.p));
+    HPV_CK(cudaIpcGetMemHandle(&h1, c->peer_flags_own.p));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handles, &h0, 64);
+    memcpy(handles + 64, &h1, 64);
+    return HPV_OK;
+}
+
+int hpv_peer_connect(hpv_ctx* c, int rank, int nranks, const unsigned char* all_handles) {
+    if (!c || !all_handles) return HPV_ERR_ARG;
+    if (nranks < 2 || nranks > HPV_MAX_PEERS || rank < 0 || rank >= nranks) return fail(c, HPV_ERR_ARG, "bad rank / nranks");
+    HPV_CK(cudaSetDevice(c->device));
+    if (!c->peer_inbox_own.p || (size_t)2 * nranks * c->peer_nvp != c->peer_inbox_own.n)
+        return fail(c, HPV_ERR_STATE, "hpv_peer_export(nranks) must be called first");
+    if (c->peer_n) return fail(c, HPV_ERR_STATE, "peer exchange is already connected");
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) { c->peer_inbox[r] = c->peer_inbox_own.p; c->peer_flags[r] = c->peer_flags_own.p; continue; }
+        cudaIpcMemHandle_t h0, h1;
+        memcpy(&h0, all_handles + (size_t)r * 128, 64);
+        memcpy(&h1, all_handles + (size_t)r * 128 + 64, 64);
+        void *q0 = nullptr, *q1 = nullptr;
+        HPV_CK(cudaIpcOpenMemHandle(&q0, h0, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_opened.push_back(q0);
+        HPV_CK(cudaIpcOpenMemHandle(&q1, h1, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_opened.push_back(q1);
+        c->peer_inbox[r] = static_cast<float*>(q0); c->peer_flags[r] = static_cast<unsigned*>(q1);
+    }
+    c->peer_rank = rank; c->peer_n = nranks; c->peer_seq = 0;
+    return HPV_OK;
+}
+
 int hpv_adam_step(hpv_ctx* c) {
     { int r = need_net(c); if (r) return r; }
     if (!c->redbuf.p) return fail(c, HPV_ERR_STATE, "hpv_loss_and_grad has not been called");
@@ -902,6 +981,7 @@ int hpv_read_losses(hpv_ctx* c, double* out, int n) {
     float h[8];
     HPV_CK(cudaMemcpyAsync(h, c->redbuf.p + c->loss_off, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     HPV_CK(cudaStreamSynchronize(c->stream));
+    { int r = check_peer_error(c); if (r) return r; }
     for (int i = 0; i < n && i < 8; ++i) out[i] = h[i];
     return HPV_OK;
 }

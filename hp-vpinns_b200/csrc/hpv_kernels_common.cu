@@ -62,38 +62,102 @@ __device__ __forceinline__ double hpv_adam_clock(const HpvAdamArgs& a, bool writ
     return (double)a.lr * sqrt(1.0 - p2) / (1.0 - p1);
 }
 
-// CTAs 0 .. nred-1 reduce 32 gradient entries each (and, with has_adam, update the parameters those entries
-// belong to); with has_loss the last CTA assembles the loss values.
+__device__ __forceinline__ unsigned long long hpv_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void hpv_st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned hpv_ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float hpv_ld_relaxed_sys(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// One warp exchanges chunk `ch` (32 entries, this lane's local value `mine`) with the other ranks and returns the
+// sum over the ranks in rank order (see HpvPeerArgs).
+__device__ __forceinline__ float hpv_peer_exchange(const HpvPeerArgs& pa, int ch, int lane, float mine) {
+    const int par = pa.seq & 1u;
+    const size_t voff = ((size_t)par * pa.nranks + pa.rank) * pa.nvp + (size_t)ch * 32 + lane;
+    for (int r = 0; r < pa.nranks; ++r) pa.inbox[r][voff] = mine;              // push (remote stores, 128 B per rank)
+    __threadfence_system();
+    __syncwarp();
+    if (lane < pa.nranks)
+        hpv_st_release_sys(pa.flags[lane] + ((size_t)par * pa.nranks + pa.rank) * pa.nchunks + ch, pa.seq);
+    if (lane < pa.nranks) {                                                     // wait for source rank `lane`
+        const unsigned* f = pa.flags[pa.rank] + ((size_t)par * pa.nranks + lane) * pa.nchunks + ch;
+        const unsigned long long t0 = hpv_globaltimer();
+        while (hpv_ld_acquire_sys(f) != pa.seq) {
+            if (hpv_globaltimer() - t0 > pa.timeout_ns) { atomicExch(pa.err, 1u); break; }
+        }
+    }
+    __syncwarp();
+    float t = 0.0f;
+    const float* in = pa.inbox[pa.rank] + (size_t)par * pa.nranks * pa.nvp + (size_t)ch * 32 + lane;
+    for (int r = 0; r < pa.nranks; ++r) t += hpv_ld_relaxed_sys(in + (size_t)r * pa.nvp);
+    return t;
+}
+
+// CTAs 0 .. nred-1 reduce 32 gradient entries each; with has_loss the last CTA assembles the loss values.  With
+// has_peer the chunk is then summed over the GPUs (the losses too), and with has_adam the parameters the chunk's
+// entries belong to are updated -- one launch for reduction, exchange and optimizer.
 __global__ void __launch_bounds__(1024) hpv_gradreduce_kernel(const HpvGradReduceArgs a, const HpvLossArgs la, int nred,
-                                                              const HpvAdamArgs ad, int has_adam) {
+                                                              const HpvAdamArgs ad, int has_adam,
+                                                              const HpvPeerArgs pa, int has_peer, int loss_chunk) {
     __shared__ __align__(16) unsigned char smem[32 * 32 * 4];
     if ((int)blockIdx.x >= nred) {
-        if (threadIdx.x < 32) hpv_losses_warp(la, threadIdx.x);
+        if (threadIdx.x < 32) {
+            hpv_losses_warp(la, threadIdx.x);
+            if (has_peer) {
+                // la.out[0..7] sits at entry 32 * loss_chunk of the reduce buffer (chunk-aligned)
+                __syncwarp();
+                const float mine = threadIdx.x < 8 ? la.out[threadIdx.x] : 0.0f;
+                const float t = hpv_peer_exchange(pa, loss_chunk, threadIdx.x, mine);
+                if (threadIdx.x < 8) la.out[threadIdx.x] = t;
+            }
+        }
         return;
     }
     HpvCta c;
     c.tid = threadIdx.x; c.nthreads = blockDim.x; c.bid = blockIdx.x; c.nblocks = nred;
     c.smem = smem; c.emu = nullptr;
-    const float g = hpv_gradreduce_body(c, a);
-    if (has_adam && threadIdx.x < 32) {
+    float g = hpv_gradreduce_body(c, a);
+    if (threadIdx.x < 32) {
         const int i = blockIdx.x * 32 + threadIdx.x;
-        const double lr_t = hpv_adam_clock(ad, i == 0);
-        if (i < a.n) {
-            const int r = ad.ref_index[i];
-            if (r >= 0) hpv_adam_one(ad, r, (double)g, lr_t);
+        if (has_peer) {
+            g = hpv_peer_exchange(pa, blockIdx.x, threadIdx.x, i < a.n ? g : 0.0f);
+            if (i < a.n) a.grad_pad[i] = g;
+        }
+        if (has_adam) {
+            const double lr_t = hpv_adam_clock(ad, i == 0);
+            if (i < a.n) {
+                const int r = ad.ref_index[i];
+                if (r >= 0) hpv_adam_one(ad, r, (double)g, lr_t);
+            }
         }
     }
 }
 
-cudaError_t hpv_launch_gradreduce(const HpvGradReduceArgs& a, const HpvLossArgs* la, const HpvAdamArgs* adam, cudaStream_t s) {
+cudaError_t hpv_launch_gradreduce(const HpvGradReduceArgs& a, const HpvLossArgs* la, const HpvAdamArgs* adam,
+                                  const HpvPeerArgs* peer, int loss_off, cudaStream_t s) {
     const int nred = (a.n + 31) / 32;
     HpvLossArgs l0;
     memset(&l0, 0, sizeof(l0));
     HpvAdamArgs a0;
     memset(&a0, 0, sizeof(a0));
+    HpvPeerArgs p0;
+    memset(&p0, 0, sizeof(p0));
     // 32 groups of partials per CTA when there are many of them (the sum is latency-bound otherwise)
     const int block = a.n_parts >= 128 ? 1024 : 256;
-    hpv_gradreduce_kernel<<<nred + (la ? 1 : 0), block, 0, s>>>(a, la ? *la : l0, nred, adam ? *adam : a0, adam ? 1 : 0);
+    hpv_gradreduce_kernel<<<nred + (la ? 1 : 0), block, 0, s>>>(a, la ? *la : l0, nred, adam ? *adam : a0, adam ? 1 : 0,
+                                                               peer ? *peer : p0, peer ? 1 : 0, loss_off / 32);
     return cudaGetLastError();
 }
 

@@ -75,9 +75,30 @@ __device__ inline void hpv_losses_warp(const HpvLossArgs& a, int lane) {
     }
 }
 #endif
+// Gradient exchange between the GPUs of one node over peer memory (NVLink / NVSwitch), fused into the reduction
+// kernel.  Every rank owns an inbox  [2 parities][nranks sources][nvp floats]  and arrival flags
+// [2][nranks][nchunks] (one per 32-entry chunk of the vector), both mapped into every peer with CUDA IPC.  A CTA
+// that has reduced its chunk of the local gradient PUSHES it into every rank's inbox (remote stores), publishes
+// the step's sequence number in the flags (release, system scope), waits for the same chunk of every other rank
+// in its OWN inbox (local polling, acquire), and sums the nranks copies in rank order -- every rank gets bitwise
+// the same sum -- before the Adam update of the chunk's parameters.  Double buffering by the parity of the
+// sequence number is enough: a rank can only be one step ahead of a rank it exchanges with.
+#define HPV_MAX_PEERS 8
+struct HpvPeerArgs {
+    int nranks, rank;
+    unsigned seq;              // >= 1, the same on every rank, +1 per exchange
+    int nvp, nchunks;          // floats per vector (padded to a multiple of 32), chunks of 32 entries
+    float* inbox[HPV_MAX_PEERS];
+    unsigned* flags[HPV_MAX_PEERS];
+    unsigned* err;             // device word, set to 1 when a wait timed out (a peer died): results are invalid
+    unsigned long long timeout_ns;
+};
+
 // la non-null: one extra CTA assembles the loss values in the same launch.  adam non-null (single-GPU training
 // step): every reduced gradient entry is consumed by the Adam update of its parameter in the same launch.
-cudaError_t hpv_launch_gradreduce(const HpvGradReduceArgs& a, const HpvLossArgs* la, const struct HpvAdamArgs* adam, cudaStream_t s);
+// peer non-null (multi-GPU training step): the reduced vector is exchanged and summed over the ranks first.
+cudaError_t hpv_launch_gradreduce(const HpvGradReduceArgs& a, const HpvLossArgs* la, const struct HpvAdamArgs* adam,
+                                  const HpvPeerArgs* peer, int loss_off, cudaStream_t s);
 struct HpvAdamArgs {
     const float* grad_pad;     // padded gradient (+ d eps at index theta_pad_n)
     const int* pad_index;      // [n_theta] reference-order index -> padded index

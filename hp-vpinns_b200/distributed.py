@@ -4,7 +4,8 @@ order, evaluates loss and gradient of its block, and ONE all-reduce of [gradient
 makes every rank hold the global values; every rank then applies the identical Adam update to its replica of the
 parameters.  No activations or residuals are ever exchanged.
 
-One process per GPU (torchrun); NCCL through torch.distributed on the same CUDA stream as the engine's kernels.
+One process per GPU (torchrun).  Default: the sum runs inside the step's last kernel over NVLink peer memory
+(`connect_peers`); `collective="nccl"` keeps the NCCL all-reduce through torch.distributed on the engine's stream.
 The point-wise losses (boundary data, PINN residual) are replicated data: only rank 0 adds them before the reduce.
 """
 import numpy as np
@@ -36,23 +37,44 @@ def reduce_tensor(engine):
     return torch.as_tensor(_DeviceBuffer(ptr, n), device="cuda")
 
 
+def connect_peers(engine, group=None):
+    """Connect the engines of the ranks of ONE node for the peer-memory gradient exchange (include/hpv.h:
+    hpv_peer_export / hpv_peer_connect): the CUDA IPC handles of every rank's inbox are gathered through
+    torch.distributed; afterwards `engine.train_steps` sums the gradient over the ranks inside its last kernel
+    (NVLink peer stores + flags) and applies Adam in the same launch -- no NCCL call per step."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world < 2:
+        return False
+    mine = engine.peer_export(world)
+    handles = [None] * world
+    dist.all_gather_object(handles, mine, group=group)
+    engine.peer_connect(rank, world, b"".join(handles))
+    dist.barrier(group=group)           # nobody pushes before every rank has mapped every inbox
+    return True
+
+
 class ShardedStep:
     """loss_and_grad -> all-reduce(SUM) -> adam_step, on the current torch CUDA stream.
 
     `engine` must have been built on this rank's element shard; `point_slots` are enabled on rank 0 only (their
     data is replicated, so summing them over ranks would count them world_size times)."""
 
-    def __init__(self, engine, group=None):
+    def __init__(self, engine, group=None, collective="peer"):
         import torch
         import torch.distributed as dist
         self.engine, self.dist, self.group = engine, dist, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.peer = False
         stream = torch.cuda.current_stream()
         if stream.cuda_stream == 0:
             raise RuntimeError("run inside `with torch.cuda.stream(torch.cuda.Stream())`: the engine needs a "
                                "non-default stream handle to share with NCCL")
         engine.set_stream(stream.cuda_stream)
         self.red = reduce_tensor(engine) if self.world > 1 else None
+        if self.world > 1 and collective == "peer":
+            self.peer = connect_peers(engine, group)
 
     def loss_and_grad(self):
         self.engine.loss_and_grad()
@@ -60,8 +82,11 @@ class ShardedStep:
             self.dist.all_reduce(self.red, group=self.group)
 
     def step(self):
-        self.loss_and_grad()
-        self.engine.adam_step()
+        if self.world == 1 or self.peer:
+            self.engine.train_steps(1, want_history=False)      # reduction, exchange and Adam in the last kernel
+        else:
+            self.loss_and_grad()
+            self.engine.adam_step()
 
 
 def allreduce_loss_grad_cpu(loss, grad, group=None):

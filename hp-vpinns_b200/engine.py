@@ -188,6 +188,18 @@ class Engine:
         self._ck(self._lib.hpv_reduce_buffer(self._h, ctypes.byref(p), ctypes.byref(n)))
         return p.value, n.value
 
+    def peer_export(self, nranks):
+        """This rank's inbox/flag IPC handles (bytes) for the peer-memory gradient exchange."""
+        buf = ctypes.create_string_buffer(128)
+        self._ck(self._lib.hpv_peer_export(self._h, int(nranks), buf))
+        return buf.raw
+
+    def peer_connect(self, rank, nranks, all_handles):
+        """all_handles: the concatenated peer_export() bytes of every rank, in rank order."""
+        if len(all_handles) != 128 * nranks:
+            raise ValueError("all_handles must hold 128 bytes per rank")
+        self._ck(self._lib.hpv_peer_connect(self._h, int(rank), int(nranks), bytes(all_handles)))
+
     def adam_step(self):
         self._ck(self._lib.hpv_adam_step(self._h))
 

@@ -112,6 +112,17 @@ int hpv_configure_training(hpv_ctx* ctx, double wv, unsigned point_slot_mask, in
 int hpv_loss_and_grad(hpv_ctx* ctx);
 int hpv_reduce_buffer(hpv_ctx* ctx, void** dev_ptr, int* n_floats);
 int hpv_adam_step(hpv_ctx* ctx);
+/* Multi-GPU (one process per GPU of ONE node): the element loss is a sum over elements (varloss_total +=
+ * loss_element, P2D:120), so each rank holds a block of elements and the ranks sum [grad | d eps | losses] once per
+ * step.  With a peer connection that sum runs INSIDE the step's last kernel over NVLink peer memory (push into
+ * every rank's inbox, flags with system-scope release/acquire, sum in rank order => bitwise identical on all
+ * ranks), followed by the Adam update in the same launch: hpv_train_steps then needs no NCCL call.
+ *   hpv_peer_export  : allocates this rank's inbox + flags, returns their two CUDA IPC handles (128 bytes).
+ *   hpv_peer_connect : all_handles = the nranks x 128 bytes gathered from every rank (rank order).
+ * Without a connection the caller all-reduces hpv_reduce_buffer itself (NCCL) between hpv_loss_and_grad and
+ * hpv_adam_step.  A rank that fails to arrive within 5 s makes the others report an error instead of hanging. */
+int hpv_peer_export(hpv_ctx* ctx, int nranks, unsigned char* handles_128_bytes);
+int hpv_peer_connect(hpv_ctx* ctx, int rank, int nranks, const unsigned char* all_handles);
 int hpv_read_losses(hpv_ctx* ctx, double* out, int n);
 int hpv_read_grad(hpv_ctx* ctx, double* grad_theta, int n, double* grad_eps);
 int hpv_reset_optimizer(hpv_ctx* ctx);
