@@ -184,33 +184,40 @@ void fill_var_args(hpv_ctx* c, HpvVarArgs& a) {
     a.bwd_done = nullptr; a.loss_scale = (float)c->wv;
 }
 
-// Choose the block size of the MLP reverse sweep: the largest number of resident threads per SM that the
-// shared-memory plan (HpvBwdSmem) allows.
-int plan_bwd(hpv_ctx* c, const HpvKernelKey& k, int& block, int& ctas_per_sm, size_t& smem) {
+// Launch plan of the MLP reverse sweep for `n_points` points: one CTA per SM of W warps, every warp running the
+// same number of 32-point tiles (hpv_mlpbwd_body).  W is bounded by the kernel's launch bounds (registers) and by
+// the shared-memory plan; among the admissible W the plan takes the fewest tiles per warp, and for that count the
+// fewest warps: at C3 (12 800 tiles on 148 SMs) 11 warps x 8 tiles instead of 12 x 8 -- the same makespan with
+// less contention and no empty tile slots -- and a handful of boundary points spread as single-warp CTAs.
+int plan_bwd(hpv_ctx* c, const HpvKernelKey& k, long long n_points, int& block, int& grid, size_t& smem) {
     HpvVarArgs va; memset(&va, 0, sizeof(va));
     va.theta_pad_n = c->net.theta_pad_n; va.nhid = c->net.nhid; va.off_wo = hpv_off_wo(c->net.dim, c->net.hp, c->net.nhid);
     HpvBwdArgs ba; memset(&ba, 0, sizeof(ba)); ba.v = va;
-    int best_threads = 0;
-    int cand[3] = {128, 256, 64};
-    int ncand = 3;
-    if (const char* ev = getenv("HPV_BWD_BLOCK")) {          // tuning override: 64, 128 or 256
-        const int v = atoi(ev);
-        if (v == 64 || v == 128 || v == 256) { cand[0] = v; ncand = 1; }
-    }
-    for (int ci = 0; ci < ncand; ++ci) {
-        HpvLaunch l; memset(&l, 0, sizeof(l));
-        long long out = 0;
-        l.kind = HPV_K_MLPBWD; l.op = 2; l.block = cand[ci]; l.bwd = &ba; l.out = &out;
+    HpvLaunch l; memset(&l, 0, sizeof(l));
+    long long out = 0;
+    l.kind = HPV_K_MLPBWD; l.bwd = &ba; l.out = &out;
+    l.op = 4;
+    HPV_CK(hpv_dispatch(k, l));
+    int wmax = (int)out / 32;
+    const long long n_wt = (n_points + 31) / 32;
+    int best_w = 0;
+    long long best_iters = 0;
+    size_t best_smem = 0;
+    int forced = 0;
+    if (const char* ev = getenv("HPV_BWD_WARPS")) forced = atoi(ev);           // tuning override
+    for (int w = wmax; w >= 1; --w) {
+        l.op = 2; l.block = 32 * w;
         HPV_CK(hpv_dispatch(k, l));
         const size_t sm = (size_t)out;
         if (sm > 227 * 1024) continue;
-        l.op = 1; l.smem = sm;
-        cudaError_t e = hpv_dispatch(k, l);
-        if (e != cudaSuccess) { cudaGetLastError(); continue; }
-        const int threads = (int)out * cand[ci];
-        if (threads > best_threads) { best_threads = threads; block = cand[ci]; ctas_per_sm = (int)out; smem = sm; }
+        const long long iters = (n_wt + (long long)c->n_sm * w - 1) / ((long long)c->n_sm * w);
+        if (forced ? (w == forced || !best_w) : (!best_w || iters <= best_iters)) { best_w = w; best_iters = iters; best_smem = sm; }
+        if (forced && w == forced) break;
     }
-    if (!best_threads) return fail(c, HPV_ERR_LIMIT, "network too deep/wide for the shared-memory plan of the MLP reverse sweep");
+    if (!best_w) return fail(c, HPV_ERR_LIMIT, "network too deep/wide for the shared-memory plan of the MLP reverse sweep");
+    block = 32 * best_w; smem = best_smem;
+    const long long n_grp = (n_wt + best_w - 1) / best_w;
+    grid = (int)(n_grp < c->n_sm ? (n_grp < 1 ? 1 : n_grp) : c->n_sm);
     return HPV_OK;
 }
 
@@ -271,11 +278,9 @@ int ensure_ready(hpv_ctx* c) {
     HPV_CK(c->loss.alloc(1));
 
     // backward launch plan
-    { int r = plan_bwd(c, bwd_key_of(c), c->bwd_block, c->bwd_ctas_per_sm, c->bwd_smem); if (r) return r; }
-    c->bwd_grid = c->n_sm * c->bwd_ctas_per_sm;
     const long long npts = (long long)c->n_el * rows * c->Q;
-    const long long ntiles = (npts + c->bwd_block - 1) / c->bwd_block;
-    if (c->bwd_grid > ntiles) c->bwd_grid = (int)ntiles;
+    { int r = plan_bwd(c, bwd_key_of(c), npts, c->bwd_block, c->bwd_grid, c->bwd_smem); if (r) return r; }
+    c->bwd_ctas_per_sm = 1;
     c->grad_stride = hpv_align4(c->net.theta_pad_n + 1);
     int max_grid = c->bwd_grid;
     if (max_grid < c->n_sm * 4) max_grid = c->n_sm * 4;          // point-loss launches reuse the buffer
@@ -375,8 +380,8 @@ int launch_points(hpv_ctx* c, int mx, int my, int n, const float* pts, float* u,
 }
 
 int launch_mlpbwd_points(hpv_ctx* c, PointSet& ps, int& grid_out) {
-    int block = 0, cps = 0; size_t smem = 0;
-    { int r = plan_bwd(c, key_of(c, ps.mx, ps.my), block, cps, smem); if (r) return r; }
+    int block = 0, grid = 0; size_t smem = 0;
+    { int r = plan_bwd(c, key_of(c, ps.mx, ps.my), ps.n, block, grid, smem); if (r) return r; }
     { int r = refresh_mirror(c, HPV_K_MLPBWD); if (r) return r; }
     HpvBwdArgs ba; memset(&ba, 0, sizeof(ba));
     HpvVarArgs& a = ba.v;
@@ -388,8 +393,6 @@ int launch_mlpbwd_points(hpv_ctx* c, PointSet& ps, int& grid_out) {
     for (int f = 0; f < HPV_NFIELDS; ++f) { a.terms[0].a0[f] = ps.a0[f]; a.terms[0].a1[f] = ps.a1[f]; }
     a.grad_part = c->grad_part.p; a.grad_stride = c->grad_stride;
     ba.Gbar = ps.gbar.p; ba.n_points = ps.n; ba.n_tiles = (ps.n + block - 1) / block; ba.pts = ps.pts.p;
-    int grid = c->n_sm * cps;
-    if (grid > ba.n_tiles) grid = ba.n_tiles;
     if ((size_t)grid * c->grad_stride > c->grad_part.n) grid = (int)(c->grad_part.n / c->grad_stride);
     HpvLaunch l; memset(&l, 0, sizeof(l));
     l.kind = HPV_K_MLPBWD; l.op = 0; l.grid = grid; l.block = block; l.smem = smem; l.stream = c->stream; l.bwd = &ba;

@@ -87,13 +87,15 @@ HPV_HD HpvF4 hpv_ld4_cg(const float* p) {
 }
 
 // Deterministic block-wide sum (fixed tree in shared memory); every thread gets the result.
-// `red` must hold nthreads floats and nthreads must be a power of two.
+// `red` must hold nthreads floats (any block size).
 HPV_HD float hpv_block_sum(const HpvCta& c, float* red, float v) {
     hpv_sync(c);
     red[c.tid] = v;
     hpv_sync(c);
-    for (int s = c.nthreads >> 1; s > 0; s >>= 1) {
-        if (c.tid < s) red[c.tid] += red[c.tid + s];
+    int top = 1;
+    while (top < c.nthreads) top <<= 1;
+    for (int s = top >> 1; s > 0; s >>= 1) {
+        if (c.tid < s && c.tid + s < c.nthreads) red[c.tid] += red[c.tid + s];
         hpv_sync(c);
     }
     float r = red[0];

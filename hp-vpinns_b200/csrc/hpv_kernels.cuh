@@ -14,15 +14,13 @@ __global__ void __launch_bounds__(HPV_THREADS, (HpvMode<DIM, MX, MY>::NCH >= 4 ?
     hpv_varfwd_body<DIM, MX, MY, HP, ACT>(c, a);
 }
 
-// Launch bounds of the reverse sweep.  The directional mode (two channels) fits 3 CTAs of 128 threads per SM
-// (168 registers, 75 KB of shared memory each); the other modes keep the full register file per thread.
-#ifndef HPV_BWD_DIR_MIN_CTAS
-#define HPV_BWD_DIR_MIN_CTAS 3         // build-time tuning knob (HPV_NVCC_EXTRA="-DHPV_BWD_DIR_MIN_CTAS=2")
-#endif
+// Launch bounds of the reverse sweep: ONE CTA per SM made of as many warps as the register file holds -- 12 in the
+// directional mode (two channels, 168 registers), 8 otherwise.  The host picks the warp count per launch
+// (plan_bwd): the warps share nothing but the constant parameters, so the CTA is only a resource container.
 template <int DIM, int MX, int MY>
 struct HpvBwdBounds {
-    static constexpr int THREADS = HpvMode<DIM, MX, MY>::DIR ? 128 : HPV_THREADS;
-    static constexpr int MIN_CTAS = HpvMode<DIM, MX, MY>::DIR ? HPV_BWD_DIR_MIN_CTAS : 1;
+    static constexpr int THREADS = HpvMode<DIM, MX, MY>::DIR ? 384 : HPV_THREADS;
+    static constexpr int MIN_CTAS = 1;
 };
 
 template <int DIM, int MX, int MY, int HP, int ACT>
@@ -88,6 +86,12 @@ static cudaError_t hpv_do(const HpvLaunch& l) {
             err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, l.block, l.smem);
             *l.out = n;
             return err;
+        }
+        if (l.op == 4) {                 // threads per block the kernel was compiled for
+            cudaFuncAttributes fa;
+            if ((err = cudaFuncGetAttributes(&fa, k)) != cudaSuccess) return err;
+            *l.out = fa.maxThreadsPerBlock;
+            return cudaSuccess;
         }
         if (l.op == 3) { void* p = nullptr; err = cudaGetSymbolAddress(&p, hpv_c_theta); *l.out = (long long)(uintptr_t)p; return err; }
         k<<<l.grid, l.block, l.smem, l.stream>>>(*l.bwd);

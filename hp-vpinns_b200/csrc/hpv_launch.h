@@ -9,7 +9,8 @@ struct HpvKernelKey { int dim, mx, my, hp, act, dir; };
 
 enum { HPV_K_VARFWD = 0, HPV_K_MLPBWD = 1, HPV_K_POINTS = 2 };
 
-// op: 0 = launch, 1 = query resident CTAs per SM for (block, smem) into *out, 2 = shared memory bytes of the
+// op: 0 = launch, 1 = query resident CTAs per SM for (block, smem) into *out, 4 = (reverse sweep) the largest
+// block size the kernel was compiled for, 2 = shared memory bytes of the
 // MLP reverse sweep for block size `block` into *out, 3 = device address of this translation unit's constant
 // parameter slots (hpv_c_theta) into *out.
 struct HpvLaunch {

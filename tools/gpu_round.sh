@@ -3,6 +3,7 @@
 # Usage (from the repo root, under gpurun): bash tools/gpu_round.sh TAG
 TAG=${1:-rXX}
 VARIANTS=${2:-}
+WARPS=${3:-}
 O=gpurun_out/$TAG
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $O/gpu.txt 2>&1
@@ -13,6 +14,9 @@ for v in $VARIANTS; do
   echo "== bench variant lib $v"; HPV_LIB=$PWD/hp-vpinns_b200/libhpv_$v.so timeout 300 python bench.py --steps 500 --no-cpu-baseline > $O/bench_$v.json 2> $O/bench_$v.err
 done
 echo "== bench c4 on one GPU"; timeout 300 python bench.py --workload c4 --steps 100 --no-cpu-baseline > $O/bench_c4.json 2> $O/bench_c4.err
+for w in $WARPS; do
+  echo "== bench HPV_BWD_WARPS=$w"; HPV_BWD_WARPS=$w timeout 300 python bench.py --steps 500 --no-cpu-baseline > $O/bench_w$w.json 2> $O/bench_w$w.err
+done
 python - <<PY
 import json,glob
 for f in sorted(glob.glob("$O/bench_*.json")):
