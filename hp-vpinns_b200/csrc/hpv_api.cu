@@ -81,6 +81,7 @@ struct hpv_ctx {
     int bwd_block = 0, bwd_grid = 0, bwd_ctas_per_sm = 0, grad_stride = 0, loss_off = 0;
     size_t bwd_smem = 0, fwd_smem = 0, adj_smem = 0;
     bool bwd_dir = true;               // allow the directional reverse sweep (HPV_BWD_DIR=0 disables)
+    int bwd_stagger_ns = 0;            // start offset between the warp rows of the reverse sweep (HPV_BWD_STAGGER_NS)
     bool adam_direct = true;           // Adam writes the constant-memory mirrors in place (HPV_ADAM_DIRECT=0 disables)
     int fwd_ctas_per_sm = 0, adj_grid = 0, slabs_per_el = 0;
     PointSet ps[HPV_MAX_POINT_SETS];
@@ -215,9 +216,20 @@ int plan_bwd(hpv_ctx* c, const HpvKernelKey& k, long long n_points, int& block, 
         if (forced && w == forced) break;
     }
     if (!best_w) return fail(c, HPV_ERR_LIMIT, "network too deep/wide for the shared-memory plan of the MLP reverse sweep");
-    block = 32 * best_w; smem = best_smem;
-    const long long n_grp = (n_wt + best_w - 1) / best_w;
-    grid = (int)(n_grp < c->n_sm ? (n_grp < 1 ? 1 : n_grp) : c->n_sm);
+    // Shape of the W warps of an SM: CTAs of 4 warps when W is a multiple of 4, one CTA of W warps otherwise.
+    // Measured (profiles/r02h, r02i): the warps of one big CTA start in lockstep and convoy through the same phases
+    // (12 warps as 1 CTA 2 251 us vs 3 CTAs 2 184 us at C4; two-tangent mode 8 warps as 1 CTA 256 us vs 2 CTAs
+    // 227 us at C3); separately launched CTAs do not.  HPV_BWD_STAGGER_NS offsets the warp rows of a big CTA instead.
+    int wcta = best_w;
+    if (best_w % 4 == 0 && best_w > 4) {
+        l.op = 2; l.block = 128;
+        HPV_CK(hpv_dispatch(k, l));
+        wcta = 4; best_smem = (size_t)out;
+    }
+    block = 32 * wcta; smem = best_smem;
+    const long long n_grp = (n_wt + wcta - 1) / wcta;
+    const long long slots = (long long)c->n_sm * (best_w / wcta);
+    grid = (int)(n_grp < slots ? (n_grp < 1 ? 1 : n_grp) : slots);
     return HPV_OK;
 }
 
@@ -280,7 +292,7 @@ int ensure_ready(hpv_ctx* c) {
     // backward launch plan
     const long long npts = (long long)c->n_el * rows * c->Q;
     { int r = plan_bwd(c, bwd_key_of(c), npts, c->bwd_block, c->bwd_grid, c->bwd_smem); if (r) return r; }
-    c->bwd_ctas_per_sm = 1;
+    c->bwd_ctas_per_sm = (c->bwd_grid + c->n_sm - 1) / c->n_sm;
     c->grad_stride = hpv_align4(c->net.theta_pad_n + 1);
     int max_grid = c->bwd_grid;
     if (max_grid < c->n_sm * 4) max_grid = c->n_sm * 4;          // point-loss launches reuse the buffer
@@ -322,6 +334,7 @@ int launch_mlpbwd_var(hpv_ctx* c) {
     const int rows = (c->net.dim == 2) ? c->Q : 1;
     ba.Gbar = c->Gbar.p; ba.n_points = c->n_el * rows * c->Q;
     ba.n_tiles = (ba.n_points + c->bwd_block - 1) / c->bwd_block; ba.pts = nullptr;
+    ba.stagger_ns = c->bwd_stagger_ns;
     HpvLaunch l; memset(&l, 0, sizeof(l));
     l.kind = HPV_K_MLPBWD; l.op = 0; l.grid = c->bwd_grid; l.block = c->bwd_block; l.smem = c->bwd_smem;
     l.stream = c->stream; l.bwd = &ba;
@@ -453,6 +466,7 @@ int hpv_create(hpv_ctx** out, int device) {
     ctx->device = device; ctx->n_sm = prop.multiProcessorCount;
     if (const char* ev = getenv("HPV_BWD_DIR")) ctx->bwd_dir = atoi(ev) != 0;
     if (const char* ev = getenv("HPV_ADAM_DIRECT")) ctx->adam_direct = atoi(ev) != 0;
+    if (const char* ev = getenv("HPV_BWD_STAGGER_NS")) ctx->bwd_stagger_ns = atoi(ev);
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete ctx;

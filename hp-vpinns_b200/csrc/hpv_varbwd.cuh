@@ -145,6 +145,7 @@ struct HpvBwdArgs {
     int n_tiles;               // tiles of blockDim points
     // scattered-point mode (boundary / PINN losses): coordinates and per-point adjoints are given directly
     const float* pts;          // [n][dim] or null (then the points are the element quadrature points)
+    int stagger_ns;            // start delay per warp "row" (warp / 4), see hpv_mlpbwd_body
 };
 
 // Compact layout of a warp's gradient accumulator (the padded parameter layout of hpv_math.cuh without the
@@ -350,6 +351,13 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
     const int grp_end = (int)(((long long)(c.bid + 1) * n_grp) / c.nblocks);
     const float* Wo = s_th + a.off_wo;
     const int g_wo = hpv_gw_wo(DIM, HP, nhid);
+#if defined(__CUDA_ARCH__)
+    // The warps of a CTA start in lockstep and run the same phase sequence: the three warps that share a scheduler
+    // (w, w+4, w+8) would ask for the same pipe at the same time.  A start offset per warp row spreads the phases.
+    // (The delay is an operand of nanosleep, not a branch: thread-dependent control flow ahead of the sweep would
+    // cost the uniform datapath, see the work partition above.)
+    if (ba.stagger_ns > 0) __nanosleep((unsigned)(warp >> 2) * (unsigned)ba.stagger_ns);
+#endif
 
 #pragma unroll 1
     for (int grp = grp_begin; grp < grp_end; ++grp) {

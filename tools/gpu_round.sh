@@ -4,6 +4,7 @@
 TAG=${1:-rXX}
 VARIANTS=${2:-}
 WARPS=${3:-}
+EXTRA=${4:-}
 O=gpurun_out/$TAG
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $O/gpu.txt 2>&1
@@ -14,6 +15,11 @@ for v in $VARIANTS; do
   echo "== bench variant lib $v"; HPV_LIB=$PWD/hp-vpinns_b200/libhpv_$v.so timeout 300 python bench.py --steps 500 --no-cpu-baseline > $O/bench_$v.json 2> $O/bench_$v.err
 done
 echo "== bench c4 on one GPU"; timeout 300 python bench.py --workload c4 --steps 100 --no-cpu-baseline > $O/bench_c4.json 2> $O/bench_c4.err
+# EXTRA: "label:ENV=VAL,ENV2=VAL2 label2:..." -> one short bench per entry with that environment
+for x in $EXTRA; do
+  lab=${x%%:*}; envs=$(echo ${x#*:} | tr ',' ' ')
+  echo "== bench $lab ($envs)"; env $envs timeout 300 python bench.py --steps 500 --no-cpu-baseline > $O/bench_$lab.json 2> $O/bench_$lab.err
+done
 for w in $WARPS; do
   echo "== bench HPV_BWD_WARPS=$w"; HPV_BWD_WARPS=$w timeout 300 python bench.py --steps 500 --no-cpu-baseline > $O/bench_w$w.json 2> $O/bench_w$w.err
 done
