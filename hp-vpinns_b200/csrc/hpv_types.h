@@ -7,7 +7,8 @@
 #define HPV_MAX_TERMS 2        // every var_form of P1D:83-91, P2D:94-115, ADI:162-174 is <= 2 projected terms
 #define HPV_NP 64              // padded number of test functions per direction (N <= 64)
 #define HPV_THREADS 256        // threads per CTA of the variational kernels
-#define HPV_CT 4               // max point tiles (of HPV_THREADS points) per chunk
+#define HPV_CT 8               // max point tiles (of HPV_THREADS points) per chunk: the projection phases (table staging,
+                               // two contractions, four barriers) are paid once per chunk
 #define HPV_MAX_HIDDEN 8       // hidden layers
 #define HPV_QMAX 128           // quadrature points per direction
 #define HPV_NTAB 4             // T*w, D1*w, D2*w, ONE

@@ -79,6 +79,7 @@ HPV_HD void hpv_adjproj_body(const HpvCta& c, const HpvAdjArgs& aa) {
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+#pragma unroll 4
             for (int k = 0; k < nty_e; ++k) {
                 const HpvF4 l4 = hpv_ld4(Lt + k * QP), b4 = hpv_ld4(s_R + k * HPV_NP + 4 * r4);
                 const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w};
@@ -111,6 +112,7 @@ HPV_HD void hpv_adjproj_body(const HpvCta& c, const HpvAdjArgs& aa) {
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+#pragma unroll 4
             for (int r = 0; r < ntx_e; ++r) {
                 const HpvF4 v4 = hpv_ld4(Vt + r * HPV_ADJ_RSP), w4 = hpv_ld4(R + r * QP);
                 const float vs[4] = {v4.x, v4.y, v4.z, v4.w}, ws[4] = {w4.x, w4.y, w4.z, w4.w};

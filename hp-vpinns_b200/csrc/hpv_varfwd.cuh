@@ -156,6 +156,7 @@ HPV_HD void hpv_varfwd_body(const HpvCta& c, const HpvVarArgs& a) {
                 const float* g = s_G + t * L.GS + jl * Q;
                 const float* R = sm + L.tab[a.terms[t].rtab] + 4 * r4;
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
                 for (int i = 0; i < Q; ++i) {
                     const float gv = g[i];
                     const HpvF4 w = hpv_ld4(R + i * HPV_NP);
@@ -172,6 +173,7 @@ HPV_HD void hpv_varfwd_body(const HpvCta& c, const HpvVarArgs& a) {
         for (int t = 0; t < a.n_terms; ++t) {
             const float* Lt = sm + L.tab[a.terms[t].ltab] + ja * HPV_NP + 4 * kt;
             const float* Pt = s_P + t * L.RMAX * HPV_NP + 4 * rt;
+#pragma unroll 4
             for (int jl = 0; jl < nrows; ++jl) {
                 const HpvF4 l4 = hpv_ld4(Lt + jl * HPV_NP), p4 = hpv_ld4(Pt + jl * HPV_NP);
                 const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, ps[4] = {p4.x, p4.y, p4.z, p4.w};
