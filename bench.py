@@ -366,7 +366,7 @@ def run_ours(args):
         eng.update_rhs_f32(Fh.data_ptr()); eng.set_params(theta_host, 0.0); eng.loss_and_grad()
         if world > 1:
             dist.all_reduce(red)
-        eng.read_losses(); eng.read_grad()
+        eng.read_losses_and_grad()
     barrier()
     t0 = time.perf_counter()
     for _ in range(n_e2e):
@@ -375,8 +375,7 @@ def run_ours(args):
         eng.loss_and_grad()
         if world > 1:
             dist.all_reduce(red)
-        lv = eng.read_losses()
-        gv, _ = eng.read_grad()
+        lv, gv, _ = eng.read_losses_and_grad()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -433,7 +432,7 @@ def run_ours(args):
                 "e2e": {"value": n_el * n_e2e / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_s / n_e2e * 1e3, "steps": n_e2e,
                         "what": "per step: hpv_update_rhs_f32 (pinned host F_ext) + hpv_set_params (host theta) + hpv_loss_and_grad "
-                                "+ hpv_read_losses + hpv_read_grad (host), wall clock"},
+                                "+ hpv_read_losses_and_grad (host), wall clock"},
                 "forward_only": {"value": n_el / (fwd_ms * 1e-3), "unit": UNIT, "ms": fwd_ms},
                 "roofline": roofline, "cpu_baseline": cpu, "loss": float(losses[0])}
         print(json.dumps(line), flush=True)

@@ -45,6 +45,7 @@ SIGNATURES = {
     "hpv_peer_connect": (c_int, [c_void_p, c_int, c_int, ctypes.c_char_p]),
     "hpv_read_losses": (c_int, [c_void_p, P_double, c_int]),
     "hpv_read_grad": (c_int, [c_void_p, P_double, c_int, P_double]),
+    "hpv_read_losses_and_grad": (c_int, [c_void_p, P_double, c_int, P_double, c_int, P_double]),
     "hpv_reset_optimizer": (c_int, [c_void_p]),
     "hpv_train_steps": (c_int, [c_void_p, c_int, P_double]),
     "hpv_launch_count": (ctypes.c_longlong, [c_void_p]),

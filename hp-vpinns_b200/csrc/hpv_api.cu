@@ -90,6 +90,10 @@ struct hpv_ctx {
     double lr = 1e-3, b1 = 0.9, b2 = 0.999, eps_hat = 1e-8;
     std::vector<float> host_f32;
     std::vector<double> host_f64;
+    // pinned staging of hpv_set_params (no host synchronisation: the copies are asynchronous and the buffer is
+    // only rewritten after `param_staged` says the previous upload has been consumed)
+    unsigned char* param_stage = nullptr; size_t param_stage_bytes = 0;
+    cudaEvent_t param_staged = nullptr; bool param_stage_busy = false;
     // constant-memory mirrors of theta_pad, one per kernel translation unit kind (forward, reverse sweep, points)
     float* mirror[3] = {nullptr, nullptr, nullptr};
     bool mirror_stale[3] = {true, true, true};
@@ -491,6 +495,8 @@ void hpv_destroy(hpv_ctx* c) {
         c->ps[s].pts.release(); c->ps[s].target.release(); c->ps[s].resid.release(); c->ps[s].gbar.release();
         c->ps[s].blk_loss.release();
     }
+    if (c->param_stage) cudaFreeHost(c->param_stage);
+    if (c->param_staged) cudaEventDestroy(c->param_staged);
     for (void* q : c->peer_opened) cudaIpcCloseMemHandle(q);
     c->peer_inbox_own.release(); c->peer_flags_own.release(); c->peer_err.release();
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -561,12 +567,24 @@ int hpv_set_params(hpv_ctx* c, const double* theta, int n, double eps) {
     std::vector<float>& pad = c->host_f32;
     hpv_pad_theta(c->net, theta, pad);
     pad.push_back((float)eps);
-    std::vector<double>& m = c->host_f64;
-    m.assign(theta, theta + n); m.push_back(eps);
-    HPV_CK(cudaMemcpyAsync(c->theta_pad.p, pad.data(), c->net.theta_pad_n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    HPV_CK(cudaMemcpyAsync(c->eps.p, pad.data() + c->net.theta_pad_n, sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    HPV_CK(cudaMemcpyAsync(c->master.p, m.data(), (n + 1) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    HPV_CK(cudaStreamSynchronize(c->stream));
+    const size_t nb_pad = pad.size() * sizeof(float), off_m = (nb_pad + 15) & ~(size_t)15, nb_m = (size_t)(n + 1) * sizeof(double);
+    if (c->param_stage_bytes < off_m + nb_m) {
+        if (c->param_stage) { HPV_CK(cudaStreamSynchronize(c->stream)); cudaFreeHost(c->param_stage); c->param_stage = nullptr; }
+        HPV_CK(cudaMallocHost(&c->param_stage, off_m + nb_m));
+        c->param_stage_bytes = off_m + nb_m;
+        if (!c->param_staged) HPV_CK(cudaEventCreateWithFlags(&c->param_staged, cudaEventDisableTiming));
+        c->param_stage_busy = false;
+    }
+    if (c->param_stage_busy) HPV_CK(cudaEventSynchronize(c->param_staged));       // previous upload consumed?
+    float* sp = reinterpret_cast<float*>(c->param_stage);
+    double* sm = reinterpret_cast<double*>(c->param_stage + off_m);
+    memcpy(sp, pad.data(), nb_pad);
+    memcpy(sm, theta, (size_t)n * sizeof(double)); sm[n] = eps;
+    HPV_CK(cudaMemcpyAsync(c->theta_pad.p, sp, c->net.theta_pad_n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    HPV_CK(cudaMemcpyAsync(c->eps.p, sp + c->net.theta_pad_n, sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    HPV_CK(cudaMemcpyAsync(c->master.p, sm, nb_m, cudaMemcpyHostToDevice, c->stream));
+    HPV_CK(cudaEventRecord(c->param_staged, c->stream));
+    c->param_stage_busy = true;
     theta_changed(c);
     return HPV_OK;
 }
@@ -1000,6 +1018,25 @@ int hpv_read_losses(hpv_ctx* c, double* out, int n) {
     HPV_CK(cudaStreamSynchronize(c->stream));
     { int r = check_peer_error(c); if (r) return r; }
     for (int i = 0; i < n && i < 8; ++i) out[i] = h[i];
+    return HPV_OK;
+}
+
+int hpv_read_losses_and_grad(hpv_ctx* c, double* losses, int nl, double* g, int n, double* ge) {
+    { int r = need_net(c); if (r) return r; }
+    if (!losses || nl < 1 || !g || n != c->net.n_theta) return fail(c, HPV_ERR_ARG, "bad output buffers");
+    if (!c->redbuf.p) return fail(c, HPV_ERR_STATE, "hpv_loss_and_grad has not been called");
+    HPV_CK(cudaSetDevice(c->device));
+    { int r = unpad_grad(c, 0); if (r) return r; }
+    std::vector<double>& gh = c->host_f64;
+    gh.resize(n + 1);
+    float h[8];
+    HPV_CK(cudaMemcpyAsync(gh.data(), c->grad_out.p, (n + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    HPV_CK(cudaMemcpyAsync(h, c->redbuf.p + c->loss_off, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    HPV_CK(cudaStreamSynchronize(c->stream));                      // the one host synchronisation of the step
+    { int r = check_peer_error(c); if (r) return r; }
+    memcpy(g, gh.data(), n * sizeof(double));
+    if (ge) *ge = gh[n];
+    for (int i = 0; i < nl && i < 8; ++i) losses[i] = h[i];
     return HPV_OK;
 }
 

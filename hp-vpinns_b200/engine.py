@@ -214,6 +214,14 @@ class Engine:
         self._ck(self._lib.hpv_read_grad(self._h, L.dptr(g), g.size, ctypes.byref(ge)))
         return g, ge.value
 
+    def read_losses_and_grad(self):
+        """(losses[6], grad, d eps) with one host synchronisation."""
+        out = np.zeros(6)
+        g = np.zeros(self.n_params)
+        ge = ctypes.c_double(0)
+        self._ck(self._lib.hpv_read_losses_and_grad(self._h, L.dptr(out), out.size, L.dptr(g), g.size, ctypes.byref(ge)))
+        return out, g, ge.value
+
     def reset_optimizer(self):
         self._ck(self._lib.hpv_reset_optimizer(self._h))
 

@@ -125,6 +125,8 @@ int hpv_peer_export(hpv_ctx* ctx, int nranks, unsigned char* handles_128_bytes);
 int hpv_peer_connect(hpv_ctx* ctx, int rank, int nranks, const unsigned char* all_handles);
 int hpv_read_losses(hpv_ctx* ctx, double* out, int n);
 int hpv_read_grad(hpv_ctx* ctx, double* grad_theta, int n, double* grad_eps);
+/* Both of the above with ONE host synchronisation (what a host-side optimizer loop needs per step). */
+int hpv_read_losses_and_grad(hpv_ctx* ctx, double* losses, int n_losses, double* grad_theta, int n, double* grad_eps);
 int hpv_reset_optimizer(hpv_ctx* ctx);
 /* nsteps full training steps (loss_and_grad + adam_step) back to back; loss_history [nsteps][6] = total, lossv
  * and the four point losses BEFORE each update (i.e. at the parameters the gradient was taken at); may be NULL. */

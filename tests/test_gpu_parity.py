@@ -134,6 +134,29 @@ def test_directional_and_two_tangent_reverse_sweeps(name, monkeypatch):
         assert np.abs(got["0"][0] - got["1"][0]).max() <= 2e-5 * np.abs(gref).max()
 
 
+def test_parameter_uploads_are_stream_ordered_and_combined_read():
+    """hpv_set_params stages the parameters in pinned memory and returns without synchronising; back-to-back
+    uploads followed by hpv_loss_and_grad + hpv_read_losses_and_grad (one synchronisation) must see each upload."""
+    c = C.load("p2d_vf1_w20")
+    inp = C.engine_inputs(c)
+    eng = G.make_engine(inp)
+    ref = G.make_engine(inp)
+    eng.configure_training(wv=1.0, point_slots=())
+    rng = np.random.default_rng(7)
+    for k in range(4):
+        theta = inp["theta"] * (1.0 + 0.02 * rng.standard_normal(inp["theta"].shape))
+        eng.set_params(inp["theta"], 0.0)           # immediately superseded by the next upload
+        eng.set_params(theta, 0.0)
+        eng.loss_and_grad()
+        losses, g, _ = eng.read_losses_and_grad()
+        ref.set_params(theta, 0.0)
+        lref = ref.varloss_forward(want_residual=False)
+        gref, _ = ref.varloss_backward()
+        assert losses[1] == pytest.approx(lref, rel=1e-6) and losses[0] == pytest.approx(lref, rel=1e-6)
+        assert np.array_equal(g, gref)
+    eng.close(); ref.close()
+
+
 def test_ragged_test_function_counts_on_gpu():
     c = C.load("p2d_vf1")
     inp = C.engine_inputs(c)
