@@ -32,6 +32,22 @@ HPV_HD void hpv_sync(const HpvCta& c) {
 #endif
 }
 
+// Programmatic dependent launch (the kernels of one training step are chained with
+// cudaLaunchAttributeProgrammaticStreamSerialization, see hpv_launch_pdl): hpv_pdl_trigger lets the next kernel of
+// the stream start its CTAs while this grid is still running; hpv_pdl_wait blocks until the previous kernel of the
+// stream has completed and its writes are visible.  Every kernel calls the wait before it touches anything the
+// previous kernel produced (no-ops when launched without the attribute, and in the host emulation).
+HPV_HD void hpv_pdl_wait() {
+#if HPV_DEVICE_CODE
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+HPV_HD void hpv_pdl_trigger() {
+#if HPV_DEVICE_CODE
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
 // Warp-level synchronisation and exchange (every lane of the warp must call them).
 HPV_HD void hpv_syncwarp(const HpvCta& c) {
 #if HPV_DEVICE_CODE

@@ -94,7 +94,7 @@ static cudaError_t hpv_do(const HpvLaunch& l) {
             return cudaSuccess;
         }
         if (l.op == 3) { void* p = nullptr; err = cudaGetSymbolAddress(&p, hpv_c_theta); *l.out = (long long)(uintptr_t)p; return err; }
-        k<<<l.grid, l.block, l.smem, l.stream>>>(*l.bwd);
+        return hpv_launch_pdl(k, l.grid, l.block, l.smem, l.stream, *l.bwd);
     } else {
         auto k = hpv_points_kernel<DIM, MX, MY, HP, ACT>;
         if ((err = hpv_prepare(k, l.smem, prepared)) != cudaSuccess) return err;

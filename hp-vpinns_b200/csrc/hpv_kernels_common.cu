@@ -22,8 +22,7 @@ cudaError_t hpv_launch_adjproj(const HpvAdjArgs& a, int grid, size_t smem, cudaS
         if (err != cudaSuccess) return err;
         prepared[dev] = smem;
     }
-    hpv_adjproj_kernel<<<grid, HPV_THREADS, smem, s>>>(a);
-    return cudaGetLastError();
+    return hpv_launch_pdl(hpv_adjproj_kernel, grid, HPV_THREADS, smem, s, a);
 }
 
 // TF1 Adam for one parameter (reference order index r; r == n_theta: eps):
@@ -112,6 +111,7 @@ __global__ void __launch_bounds__(1024) hpv_gradreduce_kernel(const HpvGradReduc
                                                               const HpvAdamArgs ad, int has_adam,
                                                               const HpvPeerArgs pa, int has_peer, int loss_chunk) {
     __shared__ __align__(16) unsigned char smem[32 * 32 * 4];
+    hpv_pdl_wait();          // everything below consumes results of the step's earlier kernels
     if ((int)blockIdx.x >= nred) {
         if (threadIdx.x < 32) {
             hpv_losses_warp(la, threadIdx.x);
@@ -156,9 +156,8 @@ cudaError_t hpv_launch_gradreduce(const HpvGradReduceArgs& a, const HpvLossArgs*
     memset(&p0, 0, sizeof(p0));
     // 32 groups of partials per CTA when there are many of them (the sum is latency-bound otherwise)
     const int block = a.n_parts >= 128 ? 1024 : 256;
-    hpv_gradreduce_kernel<<<nred + (la ? 1 : 0), block, 0, s>>>(a, la ? *la : l0, nred, adam ? *adam : a0, adam ? 1 : 0,
-                                                               peer ? *peer : p0, peer ? 1 : 0, loss_off / 32);
-    return cudaGetLastError();
+    return hpv_launch_pdl(hpv_gradreduce_kernel, nred + (la ? 1 : 0), block, 0, s, a, la ? *la : l0, nred, adam ? *adam : a0,
+                          adam ? 1 : 0, peer ? *peer : p0, peer ? 1 : 0, loss_off / 32);
 }
 
 // Stand-alone form (after the NCCL all-reduce of the multi-GPU step, and to un-pad a gradient for the host):

@@ -1,10 +1,34 @@
 // Host-side launch interface of the kernels (implemented once per padded hidden width in hpv_kernels_h*.cu).
 #pragma once
 #include <cuda_runtime.h>
+#include <stdlib.h>
+#include <string.h>
 #include "hpv_varbwd.cuh"
 #include "hpv_points.cuh"
 
 // dir != 0 (reverse sweep only): the directional mode HpvMode<2, 1, 0> instead of <2, 1, 1>.
+// Launch with programmatic stream serialisation: the kernel's CTAs may start before the previous kernel of the
+// stream has finished; the kernel orders itself with hpv_pdl_wait() (hpv_cta.cuh).  HPV_PDL=0 in the environment
+// falls back to plain launches.
+#if defined(__CUDACC__)
+inline bool hpv_pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("HPV_PDL"); on = (e && atoi(e) == 0) ? 0 : 1; }
+    return on != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t hpv_launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid, 1, 1); cfg.blockDim = dim3(block, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = hpv_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 struct HpvKernelKey { int dim, mx, my, hp, act, dir; };
 
 enum { HPV_K_VARFWD = 0, HPV_K_MLPBWD = 1, HPV_K_POINTS = 2 };

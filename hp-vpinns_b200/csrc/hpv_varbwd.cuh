@@ -50,12 +50,14 @@ HPV_HD void hpv_adjproj_body(const HpvCta& c, const HpvAdjArgs& aa) {
     if (nrows > HPV_ADJ_RS) nrows = HPV_ADJ_RS;
     const int npts_el = a.rows * Q;
 
-    for (int t = 0; t < HPV_NTAB; ++t) {
-        if (L.tab[t] < 0) continue;
+    hpv_pdl_trigger();
+    for (int t = 0; t < HPV_NTAB; ++t) {                 // the tables do not depend on the forward kernel: staged
+        if (L.tab[t] < 0) continue;                      // while its last CTAs are still running
         const float* src = a.tabN[t];
         float* dst = sm + L.tab[t];
         for (int i = tid * 4; i < HPV_NP * QP + 4; i += T * 4) hpv_st4(dst + i, hpv_ld4(src + i));
     }
+    hpv_pdl_wait();                                      // Res of the forward kernel from here on
     const int ntx_e = a.el_ntest[2 * e + 0], nty_e = a.el_ntest[2 * e + 1];
     const float rs = a.loss_scale * 2.0f / (float)(ntx_e * nty_e);
     for (int idx = tid; idx < HPV_NP * HPV_NP; idx += T) {
@@ -327,8 +329,10 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
     float* const H0 = slots_w + (size_t)(top >= 2 ? 0 : 1) * L.slot_sz;
 #define HPV_P(l) (slots_w + (size_t)((l) - 1) * L.slot_sz)
 
+    hpv_pdl_trigger();
     for (int i = lane; i < L.gwn; i += 32) s_gw[i] = 0.0f;
     if (tid < 8) s_cst[tid] = (tid == 0) ? 1.0f : 0.0f;
+    hpv_pdl_wait();                                      // Gbar (or the point adjoints) of the previous kernel
     const float eps = a.eps[0];
     float coef[HPV_MAX_TERMS][HPV_NFIELDS], coef1[HPV_MAX_TERMS][HPV_NFIELDS];      // registers: every loop over them is unrolled
 #pragma unroll
@@ -524,6 +528,7 @@ struct HpvGradReduceArgs {
 };
 
 HPV_HD float hpv_gradreduce_body(const HpvCta& c, const HpvGradReduceArgs& a) {
+    hpv_pdl_wait();                                  // the partial gradients of the reverse sweep
     float* s = reinterpret_cast<float*>(c.smem);     // [ngrp][32]
     const int li = c.tid & 31, grp = c.tid >> 5, ngrp = c.nthreads >> 5;
     const int i = c.bid * 32 + li;

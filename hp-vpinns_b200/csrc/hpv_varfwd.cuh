@@ -74,6 +74,10 @@ HPV_HD void hpv_varfwd_body(const HpvCta& c, const HpvVarArgs& a) {
     int* s_flag = reinterpret_cast<int*>(sm + L.flag);
     const int Q = a.Q;
 
+    hpv_pdl_trigger();       // the adjoint projection may stage its tables while this grid drains; this kernel itself is
+                             // launched with full stream serialisation (its parameters in constant memory were
+                             // just rewritten by the optimizer, and the constant caches are invalidated at a normal
+                             // launch boundary)
     for (int i = tid; i < Q; i += T) s_xi1[i] = a.xi1[i];
     const float eps = a.eps[0];
     float coef[HPV_MAX_TERMS][HPV_NFIELDS];              // registers: every loop over them is unrolled
