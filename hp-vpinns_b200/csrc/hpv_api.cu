@@ -280,7 +280,7 @@ int ensure_ready(hpv_ctx* c) {
         c->fwd_ctas_per_sm = (int)out;
     }
     const int rows = (c->net.dim == 2) ? c->Q : 1;
-    hpv_partition(c->part, c->n_el, rows * c->Q, HPV_THREADS, c->n_sm * c->fwd_ctas_per_sm);
+    hpv_partition(c->part, c->n_el, rows * c->Q, HPV_FWD_TILE, c->n_sm * c->fwd_ctas_per_sm, HPV_THREADS);
     { int r;
       if ((r = upload(c, c->cta_tile_begin, c->part.cta_tile_begin))) return r;
       if ((r = upload(c, c->el_first_cta, c->part.el_first_cta))) return r;

@@ -187,10 +187,14 @@ struct HpvPartition {
     std::vector<int> cta_tile_begin, el_first_cta, el_part_off, el_nparts;
 };
 
-inline void hpv_partition(HpvPartition& p, int n_el, int pts_per_el, int tile_pts, int max_ctas) {
+// Tiles of tile_pts points (never straddling elements), a contiguous range of tiles per CTA; a CTA gets at least
+// cta_pts points' worth of tiles (one full pass of its threads) unless there is less work than that.
+inline void hpv_partition(HpvPartition& p, int n_el, int pts_per_el, int tile_pts, int max_ctas, int cta_pts = 0) {
     p.tiles_per_el = (pts_per_el + tile_pts - 1) / tile_pts;
     const long long ntiles = (long long)n_el * p.tiles_per_el;
-    p.n_ctas = (int)(ntiles < max_ctas ? ntiles : max_ctas);
+    const long long per_cta = cta_pts > tile_pts ? cta_pts / tile_pts : 1;
+    const long long want = (ntiles + per_cta - 1) / per_cta;
+    p.n_ctas = (int)(want < max_ctas ? want : max_ctas);
     if (p.n_ctas < 1) p.n_ctas = 1;
     p.cta_tile_begin.resize(p.n_ctas + 1);
     for (int c = 0; c <= p.n_ctas; ++c) p.cta_tile_begin[c] = (int)((ntiles * c) / p.n_ctas);

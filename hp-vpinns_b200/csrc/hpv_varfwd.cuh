@@ -100,14 +100,18 @@ HPV_HD void hpv_varfwd_body(const HpvCta& c, const HpvVarArgs& a) {
     int t_cur = a.cta_tile_begin[c.bid];
     const int t_end = a.cta_tile_begin[c.bid + 1];
 
+    // The partition counts 32-point warp tiles (HPV_FWD_TILE), so that every CTA gets the same number of points
+    // to within one warp tile: a chunk's last pass may leave warps without points, which then issue nothing.
+    constexpr int CHUNK_TILES = HPV_CT * HPV_THREADS / HPV_FWD_TILE;
     while (t_cur < t_end) {
         const int e = t_cur / tpe, k0 = t_cur - e * tpe;
         int nt = tpe - k0;
-        if (nt > HPV_CT) nt = HPV_CT;
+        if (nt > CHUNK_TILES) nt = CHUNK_TILES;
         if (nt > t_end - t_cur) nt = t_end - t_cur;
-        const int p0 = k0 * T;
-        int p1 = (k0 + nt) * T;
+        const int p0 = k0 * HPV_FWD_TILE;
+        int p1 = (k0 + nt) * HPV_FWD_TILE;
         if (p1 > npts_el) p1 = npts_el;
+        const int npass = (p1 - p0 + T - 1) / T;
         const int ja = p0 / Q, jb = (p1 - 1) / Q, nrows = jb - ja + 1, base = ja * Q;
         const float lox = a.el_geom[4 * e + 0], hwx = a.el_geom[4 * e + 1];
         const float loy = a.el_geom[4 * e + 2], hwy = a.el_geom[4 * e + 3];
@@ -119,7 +123,7 @@ HPV_HD void hpv_varfwd_body(const HpvCta& c, const HpvVarArgs& a) {
 
         // (2) network and input derivatives at the quadrature points -> projected fields
 #pragma unroll 1
-        for (int it = 0; it < nt; ++it) {
+        for (int it = 0; it < npass; ++it) {
             const int p = p0 + it * T + tid;
             if (p < p1) {
                 const int j = p / Q, i = p - j * Q;
@@ -217,7 +221,8 @@ HPV_HD void hpv_varfwd_body(const HpvCta& c, const HpvVarArgs& a) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) S[i][j] = 0.0f;
                 const float* base_p = a.Upart + (size_t)a.el_part_off[e] * HPV_NP * HPV_NP;
-                for (int s = 0; s < nparts; ++s) {
+#pragma unroll 4
+                for (int s = 0; s < nparts; ++s) {               // (unrolled: the L2 loads of several parts in flight)
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         HpvF4 v = hpv_ld4_cg(base_p + (size_t)s * HPV_NP * HPV_NP + (4 * kt + i) * HPV_NP + 4 * rt);

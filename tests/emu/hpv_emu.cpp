@@ -166,7 +166,7 @@ int hpv_emu_varloss(int dim, const int* layers, int n_layers, int act, int Q, co
     if (F_ext) for (size_t i = 0; i < nf; ++i) F[i] = (float)F_ext[i];
     const int rows = (dim == 2) ? Q : 1;
     HpvPartition part;
-    hpv_partition(part, n_el, rows * Q, HPV_THREADS, n_ctas_fwd);
+    hpv_partition(part, n_el, rows * Q, HPV_FWD_TILE, n_ctas_fwd);          // no minimum: the tests want elements split finely
     std::vector<float> Upart((size_t)part.total_parts * HPV_NP * HPV_NP, 0.0f);
     std::vector<unsigned int> counters(n_el + 1, 0u);
     double loss = 0.0;
