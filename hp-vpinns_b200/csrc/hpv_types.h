@@ -7,7 +7,9 @@
 #define HPV_MAX_TERMS 2        // every var_form of P1D:83-91, P2D:94-115, ADI:162-174 is <= 2 projected terms
 #define HPV_NP 64              // padded number of test functions per direction (N <= 64)
 #define HPV_THREADS 256        // threads per CTA of the variational kernels
-#define HPV_FWD_TILE 32        // granularity of the forward kernel's work partition (points)
+#define HPV_FWD_TILE 256       // granularity of the forward kernel's work partition (points).  32 (warp tiles: every CTA
+                               // the same number of points) measured no faster at C3 and 2 % slower at C4
+                               // (profiles/r02m): a warp runs the same number of passes either way
 #define HPV_CT 8               // max point tiles (of HPV_THREADS points) per chunk: the projection phases (table staging,
                                // two contractions, four barriers) are paid once per chunk
 #define HPV_MAX_HIDDEN 8       // hidden layers

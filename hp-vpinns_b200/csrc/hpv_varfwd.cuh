@@ -100,8 +100,7 @@ HPV_HD void hpv_varfwd_body(const HpvCta& c, const HpvVarArgs& a) {
     int t_cur = a.cta_tile_begin[c.bid];
     const int t_end = a.cta_tile_begin[c.bid + 1];
 
-    // The partition counts 32-point warp tiles (HPV_FWD_TILE), so that every CTA gets the same number of points
-    // to within one warp tile: a chunk's last pass may leave warps without points, which then issue nothing.
+    // The partition counts tiles of HPV_FWD_TILE points; a chunk's last pass may leave warps without points.
     constexpr int CHUNK_TILES = HPV_CT * HPV_THREADS / HPV_FWD_TILE;
     while (t_cur < t_end) {
         const int e = t_cur / tpe, k0 = t_cur - e * tpe;
