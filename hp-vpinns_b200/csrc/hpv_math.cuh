@@ -194,68 +194,99 @@ HPV_HD void hpv_act2m(hpv_pair zv, hpv_pair& a, hpv_pair& s1, hpv_pair& s2, hpv_
     }
 }
 
-// Pre-activations (z, dz, d2z) [or a mixed state] -> post-activations (h, dh, d2h), in place, on packed pairs.
+// One pair of units m of hpv_activate / hpv_activate_bwd (below), results in o.  The fused compute-and-store
+// helpers of hpv_slot.cuh use them quad by quad, so that a stored state never has to exist as a whole in
+// registers (which would have to be gathered into aligned quads for the 128-bit stores, one MOV per register).
+template <int DIM, int MX, int MY>
+struct HpvPairOut { hpv_pair v, dx, dy, ex, ey; };
+
 //   h = s(z);  dh = s'(z) dz;  d2h = s''(z) dz^2 + s'(z) d2z
-template <int DIM, int MX, int MY, int HP, int ACT, bool MIXED = false>
-HPV_HD void hpv_activate(HpvState<DIM, MX, MY, HP>& s) {
+template <int DIM, int MX, int MY, int HP, int ACT, bool MIXED>
+HPV_HD void hpv_activate_pair(const HpvState<DIM, MX, MY, HP>& s, int m, HpvPairOut<DIM, MX, MY>& o) {
     typedef HpvMode<DIM, MX, MY> M;
-#pragma unroll
-    for (int m = 0; m < HP / 2; ++m) {
-        hpv_pair a, s1, s2, s3;
-        hpv_act2m<ACT, MIXED>(s.v.p[m], a, s1, s2, s3, false);
-        s.v.p[m] = a;
-        if constexpr (M::DX) {
-            const hpv_pair dz = s.dx.p[m];
-            if constexpr (M::EX) s.ex.p[m] = hpv_fma2r(hpv_mul2(s2, dz), dz, hpv_mul2(s1, s.ex.p[m]));
-            s.dx.p[m] = hpv_mul2(s1, dz);
-        }
-        if constexpr (M::DY) {
-            const hpv_pair dz = s.dy.p[m];
-            if constexpr (M::EY) s.ey.p[m] = hpv_fma2r(hpv_mul2(s2, dz), dz, hpv_mul2(s1, s.ey.p[m]));
-            s.dy.p[m] = hpv_mul2(s1, dz);
-        }
+    hpv_pair a, s1, s2, s3;
+    hpv_act2m<ACT, MIXED>(s.v.p[m], a, s1, s2, s3, false);
+    o.v = a;
+    if constexpr (M::DX) {
+        const hpv_pair dz = s.dx.p[m];
+        if constexpr (M::EX) o.ex = hpv_fma2r(hpv_mul2(s2, dz), dz, hpv_mul2(s1, s.ex.p[m]));
+        o.dx = hpv_mul2(s1, dz);
+    }
+    if constexpr (M::DY) {
+        const hpv_pair dz = s.dy.p[m];
+        if constexpr (M::EY) o.ey = hpv_fma2r(hpv_mul2(s2, dz), dz, hpv_mul2(s1, s.ey.p[m]));
+        o.dy = hpv_mul2(s1, dz);
     }
 }
 
-// Reverse of hpv_activate.  In: pre-activations z (value + tangents) and the adjoints of the post-activations
-// (g).  Out (in place in g): adjoints of the pre-activations.
+// Reverse of the above for pair m.  In: z (pre-activations or a mixed state) and the adjoints g of the
+// post-activations.  Out: adjoints of the pre-activations.
 //   zbar   = hbar s1 + sum_d [ dhbar_d s2 dz_d + d2hbar_d (s3 dz_d^2 + s2 d2z_d) ]
 //   dzbar  = dhbar s1 + 2 d2hbar s2 dz
 //   d2zbar = d2hbar s1
 // with s1, s2, s3 the first three derivatives of the activation at z (tanh: s2 = -2 a s1, s3 = -2 s1 (1 - 3 a^2)).
-// MIXED: z is a mixed state (see hpv_to_mixed).
-template <int DIM, int MX, int MY, int HP, int ACT, bool MIXED = false>
-HPV_HD void hpv_activate_bwd(const HpvState<DIM, MX, MY, HP>& z, HpvState<DIM, MX, MY, HP>& g) {
+template <int DIM, int MX, int MY, int HP, int ACT, bool MIXED>
+HPV_HD void hpv_activate_bwd_pair(const HpvState<DIM, MX, MY, HP>& z, const HpvState<DIM, MX, MY, HP>& g, int m,
+                                  HpvPairOut<DIM, MX, MY>& o) {
     typedef HpvMode<DIM, MX, MY> M;
+    hpv_pair a, s1, s2, s3;
+    hpv_act2m<ACT, MIXED>(z.v.p[m], a, s1, s2, s3, M::EX || M::EY);
+    hpv_pair zb = hpv_mul2(g.v.p[m], s1);
+    if constexpr (M::DX) {
+        const hpv_pair dz = z.dx.p[m], gd = g.dx.p[m];
+        zb = hpv_fma2r(hpv_mul2(gd, s2), dz, zb);
+        hpv_pair dzb = hpv_mul2(gd, s1);
+        if constexpr (M::EX) {
+            const hpv_pair d2z = z.ex.p[m], ge = g.ex.p[m];
+            zb = hpv_fma2r(ge, hpv_fma2r(hpv_mul2(s3, dz), dz, hpv_mul2(s2, d2z)), zb);
+            dzb = hpv_fma2r(hpv_mul2(hpv_mul2(ge, s2), hpv_dup(2.0f)), dz, dzb);
+            o.ex = hpv_mul2(ge, s1);
+        }
+        o.dx = dzb;
+    }
+    if constexpr (M::DY) {
+        const hpv_pair dz = z.dy.p[m], gd = g.dy.p[m];
+        zb = hpv_fma2r(hpv_mul2(gd, s2), dz, zb);
+        hpv_pair dzb = hpv_mul2(gd, s1);
+        if constexpr (M::EY) {
+            const hpv_pair d2z = z.ey.p[m], ge = g.ey.p[m];
+            zb = hpv_fma2r(ge, hpv_fma2r(hpv_mul2(s3, dz), dz, hpv_mul2(s2, d2z)), zb);
+            dzb = hpv_fma2r(hpv_mul2(hpv_mul2(ge, s2), hpv_dup(2.0f)), dz, dzb);
+            o.ey = hpv_mul2(ge, s1);
+        }
+        o.dy = dzb;
+    }
+    o.v = zb;
+}
+
+template <int DIM, int MX, int MY, int HP>
+HPV_HD void hpv_put_pair(HpvState<DIM, MX, MY, HP>& s, int m, const HpvPairOut<DIM, MX, MY>& o) {
+    typedef HpvMode<DIM, MX, MY> M;
+    s.v.p[m] = o.v;
+    if constexpr (M::DX) s.dx.p[m] = o.dx;
+    if constexpr (M::DY) s.dy.p[m] = o.dy;
+    if constexpr (M::EX) s.ex.p[m] = o.ex;
+    if constexpr (M::EY) s.ey.p[m] = o.ey;
+}
+
+// Pre-activations (z, dz, d2z) [or a mixed state] -> post-activations (h, dh, d2h), in place.
+template <int DIM, int MX, int MY, int HP, int ACT, bool MIXED = false>
+HPV_HD void hpv_activate(HpvState<DIM, MX, MY, HP>& s) {
 #pragma unroll
     for (int m = 0; m < HP / 2; ++m) {
-        hpv_pair a, s1, s2, s3;
-        hpv_act2m<ACT, MIXED>(z.v.p[m], a, s1, s2, s3, M::EX || M::EY);
-        hpv_pair zb = hpv_mul2(g.v.p[m], s1);
-        if constexpr (M::DX) {
-            const hpv_pair dz = z.dx.p[m], gd = g.dx.p[m];
-            zb = hpv_fma2r(hpv_mul2(gd, s2), dz, zb);
-            hpv_pair dzb = hpv_mul2(gd, s1);
-            if constexpr (M::EX) {
-                const hpv_pair d2z = z.ex.p[m], ge = g.ex.p[m];
-                zb = hpv_fma2r(ge, hpv_fma2r(hpv_mul2(s3, dz), dz, hpv_mul2(s2, d2z)), zb);
-                dzb = hpv_fma2r(hpv_mul2(hpv_mul2(ge, s2), hpv_dup(2.0f)), dz, dzb);
-                g.ex.p[m] = hpv_mul2(ge, s1);
-            }
-            g.dx.p[m] = dzb;
-        }
-        if constexpr (M::DY) {
-            const hpv_pair dz = z.dy.p[m], gd = g.dy.p[m];
-            zb = hpv_fma2r(hpv_mul2(gd, s2), dz, zb);
-            hpv_pair dzb = hpv_mul2(gd, s1);
-            if constexpr (M::EY) {
-                const hpv_pair d2z = z.ey.p[m], ge = g.ey.p[m];
-                zb = hpv_fma2r(ge, hpv_fma2r(hpv_mul2(s3, dz), dz, hpv_mul2(s2, d2z)), zb);
-                dzb = hpv_fma2r(hpv_mul2(hpv_mul2(ge, s2), hpv_dup(2.0f)), dz, dzb);
-                g.ey.p[m] = hpv_mul2(ge, s1);
-            }
-            g.dy.p[m] = dzb;
-        }
-        g.v.p[m] = zb;
+        HpvPairOut<DIM, MX, MY> o;
+        hpv_activate_pair<DIM, MX, MY, HP, ACT, MIXED>(s, m, o);
+        hpv_put_pair<DIM, MX, MY, HP>(s, m, o);
+    }
+}
+
+// Reverse of hpv_activate, in place in g (z: pre-activations, or a mixed state with MIXED).
+template <int DIM, int MX, int MY, int HP, int ACT, bool MIXED = false>
+HPV_HD void hpv_activate_bwd(const HpvState<DIM, MX, MY, HP>& z, HpvState<DIM, MX, MY, HP>& g) {
+#pragma unroll
+    for (int m = 0; m < HP / 2; ++m) {
+        HpvPairOut<DIM, MX, MY> o;
+        hpv_activate_bwd_pair<DIM, MX, MY, HP, ACT, MIXED>(z, g, m, o);
+        hpv_put_pair<DIM, MX, MY, HP>(g, m, o);
     }
 }

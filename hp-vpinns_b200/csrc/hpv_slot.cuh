@@ -65,6 +65,45 @@ HPV_HD void hpv_store_state(float* slot, int T, int tid, const HpvState<DIM, MX,
     });
 }
 
+// Store the channels of two pair results (units 4*j4 .. 4*j4+3) with one 128-bit store per channel.
+template <int DIM, int MX, int MY, int HP>
+HPV_HD void hpv_store_quad(float* slot, int T, int tid, int j4, const HpvPairOut<DIM, MX, MY>& a, const HpvPairOut<DIM, MX, MY>& b) {
+    typedef HpvMode<DIM, MX, MY> M;
+    constexpr int SP = HpvSP<HP>::value;
+    float* row = slot + (size_t)tid * SP + 4 * j4;
+    hpv_st_pairs(row + (size_t)M::C_V * T * SP, a.v, b.v);
+    if constexpr (M::DX) hpv_st_pairs(row + (size_t)M::C_DX * T * SP, a.dx, b.dx);
+    if constexpr (M::DY) hpv_st_pairs(row + (size_t)M::C_DY * T * SP, a.dy, b.dy);
+    if constexpr (M::EX) hpv_st_pairs(row + (size_t)M::C_EX * T * SP, a.ex, b.ex);
+    if constexpr (M::EY) hpv_st_pairs(row + (size_t)M::C_EY * T * SP, a.ey, b.ey);
+}
+
+// hpv_activate followed by hpv_store_state of the result, quad by quad: the post-activations go straight from the
+// arithmetic into the store operands and never exist as a whole state in registers.  s is left unchanged.
+template <int DIM, int MX, int MY, int HP, int ACT, bool MIXED>
+HPV_HD void hpv_activate_store(const HpvState<DIM, MX, MY, HP>& s, float* slot, int T, int tid) {
+#pragma unroll
+    for (int j4 = 0; j4 < HP / 4; ++j4) {
+        HpvPairOut<DIM, MX, MY> a, b;
+        hpv_activate_pair<DIM, MX, MY, HP, ACT, MIXED>(s, 2 * j4, a);
+        hpv_activate_pair<DIM, MX, MY, HP, ACT, MIXED>(s, 2 * j4 + 1, b);
+        hpv_store_quad<DIM, MX, MY, HP>(slot, T, tid, j4, a, b);
+    }
+}
+
+// hpv_activate_bwd followed by hpv_store_state of the resulting adjoints, quad by quad (g is left unchanged; it is
+// dead afterwards in the reverse sweep: the next product overwrites it).
+template <int DIM, int MX, int MY, int HP, int ACT, bool MIXED>
+HPV_HD void hpv_activate_bwd_store(const HpvState<DIM, MX, MY, HP>& z, const HpvState<DIM, MX, MY, HP>& g, float* slot, int T, int tid) {
+#pragma unroll
+    for (int j4 = 0; j4 < HP / 4; ++j4) {
+        HpvPairOut<DIM, MX, MY> a, b;
+        hpv_activate_bwd_pair<DIM, MX, MY, HP, ACT, MIXED>(z, g, 2 * j4, a);
+        hpv_activate_bwd_pair<DIM, MX, MY, HP, ACT, MIXED>(z, g, 2 * j4 + 1, b);
+        hpv_store_quad<DIM, MX, MY, HP>(slot, T, tid, j4, a, b);
+    }
+}
+
 template <int DIM, int MX, int MY, int HP>
 HPV_HD void hpv_load_state(const float* slot, int T, int tid, HpvState<DIM, MX, MY, HP>& s) {
     typedef HpvMode<DIM, MX, MY> M;
@@ -163,14 +202,12 @@ HPV_HD void hpv_net_point_slot(const float* th, int nhid, int off_wo, float x, f
                                float f[HPV_NFIELDS]) {
     HpvState<DIM, MX, MY, HP> s;
     hpv_layer1_pre<DIM, MX, MY, HP>(th, x, y, s);
-    hpv_activate<DIM, MX, MY, HP, ACT>(s);
-    hpv_store_state<DIM, MX, MY, HP>(slot, T, tid, s);
+    hpv_activate_store<DIM, MX, MY, HP, ACT, false>(s, slot, T, tid);
 #pragma unroll 1
     for (int l = 1; l < nhid; ++l) {
         const float* W = th + hpv_off_wl(DIM, HP, l);
         hpv_matmul_slot<DIM, MX, MY, HP>(W, W + HP * HP, slot, T, tid, s);
-        hpv_activate<DIM, MX, MY, HP, ACT>(s);
-        hpv_store_state<DIM, MX, MY, HP>(slot, T, tid, s);
+        hpv_activate_store<DIM, MX, MY, HP, ACT, false>(s, slot, T, tid);
     }
     hpv_output_slot<DIM, MX, MY, HP>(th + off_wo, slot, T, tid, f);
 }

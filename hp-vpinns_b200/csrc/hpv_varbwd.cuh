@@ -412,17 +412,12 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
         for (int l = 1; l <= top; ++l, woff += 2 * HP * HP + HP) {
             hpv_to_mixed<DIM, MX, MY, HP, ACT>(pre);                     // mixed state of layer l-1
             if (l >= 2) hpv_store_state<DIM, MX, MY, HP>(HPV_P(l - 1), 32, lane, pre);
-            hpv_activate<DIM, MX, MY, HP, ACT, true>(pre);               // h_{l-1}
-            hpv_store_state<DIM, MX, MY, HP>(X, 32, lane, pre);
+            hpv_activate_store<DIM, MX, MY, HP, ACT, true>(pre, X, 32, lane);     // h_{l-1}
             const float* W = s_th + woff;
             hpv_matmul_slot<DIM, MX, MY, HP>(W, W + HP * HP, X, 32, lane, pre);
         }
         hpv_to_mixed<DIM, MX, MY, HP, ACT>(pre);                         // pre = mixed state of the top layer from here on
-        {
-            State h = pre;
-            hpv_activate<DIM, MX, MY, HP, ACT, true>(h);
-            hpv_store_state<DIM, MX, MY, HP>(X, 32, lane, h);
-        }
+        hpv_activate_store<DIM, MX, MY, HP, ACT, true>(pre, X, 32, lane);         // h_top
         // d loss / d eps needs the fields themselves; the directional mode is only chosen for forms without an
         // eps-dependent coefficient (hpv_form_directional), where this sum is identically 0
         if constexpr (!M::DIR) {
@@ -460,16 +455,11 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
         int woff_t = a.off_wo - HP * HP;                             // = hpv_off_wt(DIM, HP, top)
 #pragma unroll 1
         for (int l = top; l >= 1; --l, woff_t -= 2 * HP * HP + HP) {
-            hpv_activate_bwd<DIM, MX, MY, HP, ACT, true>(pre, g);       // g := adjoint of the pre-activations of layer l
-            hpv_store_state<DIM, MX, MY, HP>(X, 32, lane, g);
+            hpv_activate_bwd_store<DIM, MX, MY, HP, ACT, true>(pre, g, X, 32, lane);   // X := adjoint of the pre-activations of layer l
             float* INl = (l - 1 >= 1) ? HPV_P(l - 1) : H0;
             if (l - 1 >= 1) hpv_load_state<DIM, MX, MY, HP>(INl, 32, lane, pre);   // mixed state of layer l-1
             else { HPV_LAYER1(pre); hpv_to_mixed<DIM, MX, MY, HP, ACT>(pre); }
-            {
-                State h = pre;
-                hpv_activate<DIM, MX, MY, HP, ACT, true>(h);            // h_{l-1}: left factor of the W_l gradient
-                hpv_store_state<DIM, MX, MY, HP>(INl, 32, lane, h);
-            }
+            hpv_activate_store<DIM, MX, MY, HP, ACT, true>(pre, INl, 32, lane);   // h_{l-1}: left factor of the W_l gradient
             hpv_syncwarp(c);
             float* gW = s_gw + hpv_gw_wl(DIM, HP, l);
             hpv_wgrad_warp<SP, SP, M::NCH, HP, HP / 4, 4, true, 0, HP, DIM>(c, INl, X, gW, gW + HP * HP, s_cst);
@@ -479,8 +469,7 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
         }
 
         // ---- first layer ----
-        hpv_activate_bwd<DIM, MX, MY, HP, ACT, true>(pre, g);
-        hpv_store_state<DIM, MX, MY, HP>(X, 32, lane, g);
+        hpv_activate_bwd_store<DIM, MX, MY, HP, ACT, true>(pre, g, X, 32, lane);
         {
             HpvF4 o;
             o.x = x; o.y = y; o.z = 1.0f; o.w = 0.0f; hpv_st4(s_in0 + (0 * 32 + lane) * 4, o);
