@@ -202,12 +202,14 @@ HPV_HD void hpv_net_point_slot(const float* th, int nhid, int off_wo, float x, f
                                float f[HPV_NFIELDS]) {
     HpvState<DIM, MX, MY, HP> s;
     hpv_layer1_pre<DIM, MX, MY, HP>(th, x, y, s);
-    hpv_activate_store<DIM, MX, MY, HP, ACT, false>(s, slot, T, tid);
+    hpv_activate<DIM, MX, MY, HP, ACT>(s);
+    hpv_store_state<DIM, MX, MY, HP>(slot, T, tid, s);
 #pragma unroll 1
     for (int l = 1; l < nhid; ++l) {
         const float* W = th + hpv_off_wl(DIM, HP, l);
         hpv_matmul_slot<DIM, MX, MY, HP>(W, W + HP * HP, slot, T, tid, s);
-        hpv_activate_store<DIM, MX, MY, HP, ACT, false>(s, slot, T, tid);
+        hpv_activate<DIM, MX, MY, HP, ACT>(s);        // (the fused hpv_activate_store measured 3 % slower here, r02n)
+        hpv_store_state<DIM, MX, MY, HP>(slot, T, tid, s);
     }
     hpv_output_slot<DIM, MX, MY, HP>(th + off_wo, slot, T, tid, f);
 }
