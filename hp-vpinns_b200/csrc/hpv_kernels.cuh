@@ -14,12 +14,23 @@ __global__ void __launch_bounds__(HPV_THREADS, (HpvMode<DIM, MX, MY>::NCH >= 4 ?
     hpv_varfwd_body<DIM, MX, MY, HP, ACT>(c, a);
 }
 
-// Launch bounds of the reverse sweep: ONE CTA per SM made of as many warps as the register file holds -- 12 in the
-// directional mode (two channels, 168 registers), 8 otherwise.  The host picks the warp count per launch
-// (plan_bwd): the warps share nothing but the constant parameters, so the CTA is only a resource container.
+// Launch bounds of the reverse sweep.  The host picks the number of warps per SM and their grouping into CTAs per
+// launch (plan_bwd): the warps share nothing but the constant parameters, so a CTA is only a resource container.
+// The kernel is bound by shared-memory / constant-load latency, so resident warps matter more than registers:
+// with one or two channels (incl. the directional mode of the headline form) it is compiled for 512 threads = 128
+// registers -- ptxas fits it with the same ~90 bytes of spills it has at 168, and 15-16 warps per SM instead of
+// 11-12 took C3 from 146 to 135 us (profiles/r02o) --, with three channels for 384 threads = 168 registers (no
+// spills), with four or five for 256 threads (255 registers; 168 would spill 2 KB per thread).
+#ifndef HPV_BWD_THREADS_2CH
+#define HPV_BWD_THREADS_2CH 512
+#endif
+#ifndef HPV_BWD_THREADS_3CH
+#define HPV_BWD_THREADS_3CH 384
+#endif
 template <int DIM, int MX, int MY>
 struct HpvBwdBounds {
-    static constexpr int THREADS = HpvMode<DIM, MX, MY>::DIR ? 384 : HPV_THREADS;
+    static constexpr int NCH = HpvMode<DIM, MX, MY>::NCH;
+    static constexpr int THREADS = NCH <= 2 ? HPV_BWD_THREADS_2CH : (NCH == 3 ? HPV_BWD_THREADS_3CH : HPV_THREADS);
     static constexpr int MIN_CTAS = 1;
 };
 

@@ -177,14 +177,13 @@ struct HpvBwdSmem {
     typedef HpvMode<DIM, MX, MY> M;
     static constexpr int SP = HpvSP<HP>::value;
     static constexpr int NCH1 = 1 + (M::DX ? 1 : 0) + (M::DY ? 1 : 0);     // channels with a non-zero seed at layer 1
-    int cst, slots, in0, go, gw, red, total, NS, slot_sz, gwn;
+    int cst, slots, go, gw, red, total, NS, slot_sz, gwn;
     HPV_HD HpvBwdSmem(int nhid, int T) {
         int o = 0;
         cst = o; o += 8;                                   // {1,0,0,0} (bias row of the value channel), {0,0,0,0}
         NS = nhid - 1 > 2 ? nhid - 1 : 2;
         slot_sz = M::NCH * T * SP;
         slots = o; o += NS * slot_sz;
-        in0 = o; o += NCH1 * T * 4;
         go = o; o += hpv_align4(M::NCH * T);
         gwn = hpv_gw_n(DIM, HP, nhid);
         gw = o; o += (T / 32) * gwn;
@@ -314,7 +313,6 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
     // compile-time strides (the slot helpers are called with T = 32, tid = lane).
     constexpr int NCH1 = HpvBwdSmem<DIM, MX, MY, HP>::NCH1;
     constexpr int WSLOT = M::NCH * 32 * SP;
-    float* s_in0 = sm + L.in0 + warp * (NCH1 * 32 * 4);
     float* s_go = sm + L.go + warp * (M::NCH * 32);
     float* s_red = sm + L.red;
     // Slots (one row of SP floats per thread and channel).  P(l), l = 1..top-1: pre-activations of hidden layer l
@@ -327,6 +325,9 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
     float* const slots_w = sm + L.slots + warp * WSLOT;
     float* const X = slots_w + (size_t)(top >= 1 ? top - 1 : 0) * L.slot_sz;
     float* const H0 = slots_w + (size_t)(top >= 2 ? 0 : 1) * L.slot_sz;
+    // layer-1 inputs of the first-layer gradient ([channel][32][4]): written when H0 is dead, in its place
+    float* const s_in0 = H0;
+    static_assert(NCH1 * 4 <= M::NCH * SP, "the layer-1 input rows must fit into a slot");
 #define HPV_P(l) (slots_w + (size_t)((l) - 1) * L.slot_sz)
 
     hpv_pdl_trigger();

@@ -22,6 +22,9 @@ for x in $EXTRA; do
 done
 for w in $WARPS; do
   echo "== bench HPV_BWD_WARPS=$w"; HPV_BWD_WARPS=$w timeout 300 python bench.py --steps 500 --no-cpu-baseline > $O/bench_w$w.json 2> $O/bench_w$w.err
+  for v in $VARIANTS; do
+    HPV_LIB=$PWD/hp-vpinns_b200/libhpv_$v.so HPV_BWD_WARPS=$w timeout 300 python bench.py --steps 500 --no-cpu-baseline > $O/bench_${v}_w$w.json 2> $O/bench_${v}_w$w.err
+  done
 done
 python - <<PY
 import json,glob
