@@ -225,7 +225,13 @@ int plan_bwd(hpv_ctx* c, const HpvKernelKey& k, long long n_points, int& block, 
     // (12 warps as 1 CTA 2 251 us vs 3 CTAs 2 184 us at C4; two-tangent mode 8 warps as 1 CTA 256 us vs 2 CTAs
     // 227 us at C3); separately launched CTAs do not.  HPV_BWD_STAGGER_NS offsets the warp rows of a big CTA instead.
     int wcta = best_w;
-    if (best_w % 4 == 0 && best_w > 4) {
+    int force_cta = 0;
+    if (const char* ev = getenv("HPV_BWD_CTA_WARPS")) force_cta = atoi(ev);      // tuning override: warps per CTA
+    if (force_cta > 0 && best_w % force_cta == 0) {
+        l.op = 2; l.block = 32 * force_cta;
+        HPV_CK(hpv_dispatch(k, l));
+        wcta = force_cta; best_smem = (size_t)out;
+    } else if (best_w % 4 == 0 && best_w > 4) {
         l.op = 2; l.block = 128;
         HPV_CK(hpv_dispatch(k, l));
         wcta = 4; best_smem = (size_t)out;

@@ -50,7 +50,6 @@ HPV_HD void hpv_adjproj_body(const HpvCta& c, const HpvAdjArgs& aa) {
     if (nrows > HPV_ADJ_RS) nrows = HPV_ADJ_RS;
     const int npts_el = a.rows * Q;
 
-    hpv_pdl_trigger();
     for (int t = 0; t < HPV_NTAB; ++t) {                 // the tables do not depend on the forward kernel: staged
         if (L.tab[t] < 0) continue;                      // while its last CTAs are still running
         const float* src = a.tabN[t];
@@ -137,6 +136,7 @@ HPV_HD void hpv_adjproj_body(const HpvCta& c, const HpvAdjArgs& aa) {
             }
         }
     }
+    hpv_pdl_trigger();       // at the end, see hpv_varfwd_body
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -330,7 +330,6 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
     static_assert(NCH1 * 4 <= M::NCH * SP, "the layer-1 input rows must fit into a slot");
 #define HPV_P(l) (slots_w + (size_t)((l) - 1) * L.slot_sz)
 
-    hpv_pdl_trigger();
     for (int i = lane; i < L.gwn; i += 32) s_gw[i] = 0.0f;
     if (tid < 8) s_cst[tid] = (tid == 0) ? 1.0f : 0.0f;
     hpv_pdl_wait();                                      // Gbar (or the point adjoints) of the previous kernel
@@ -492,6 +491,7 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
     }
 #undef HPV_P
 
+    hpv_pdl_trigger();       // the sweep of this CTA is done (at the end, see hpv_varfwd_body)
     // ---- publish this CTA's partial gradient: the warps' accumulators summed in a fixed order, padded layout ----
     const float dtot = hpv_block_sum(c, s_red, deps);
     float* gpart = a.grad_part + (size_t)c.bid * a.grad_stride;

@@ -74,10 +74,6 @@ HPV_HD void hpv_varfwd_body(const HpvCta& c, const HpvVarArgs& a) {
     int* s_flag = reinterpret_cast<int*>(sm + L.flag);
     const int Q = a.Q;
 
-    hpv_pdl_trigger();       // the adjoint projection may stage its tables while this grid drains; this kernel itself is
-                             // launched with full stream serialisation (its parameters in constant memory were
-                             // just rewritten by the optimizer, and the constant caches are invalidated at a normal
-                             // launch boundary)
     for (int i = tid; i < Q; i += T) s_xi1[i] = a.xi1[i];
     const float eps = a.eps[0];
     float coef[HPV_MAX_TERMS][HPV_NFIELDS];              // registers: every loop over them is unrolled
@@ -273,4 +269,11 @@ HPV_HD void hpv_varfwd_body(const HpvCta& c, const HpvVarArgs& a) {
         }
         hpv_sync(c);
     }
+    // This CTA is done: the next kernel of the step (adjoint projection) may start taking the SM's resources and
+    // stage its tables while the remaining CTAs of this grid finish.  The trigger sits at the END of the work on
+    // purpose: triggered at the start, the CTAs of a dependent kernel become resident as soon as they fit and then
+    // idle at their wait, displacing CTAs of this grid that have not been scheduled yet (measured at C4, r02q:
+    // +20 % step time).  This kernel itself is launched with full stream serialisation: its parameters in constant
+    // memory were just rewritten by the optimizer, and the constant caches are invalidated at a normal launch.
+    hpv_pdl_trigger();
 }
