@@ -215,26 +215,25 @@ int plan_bwd(hpv_ctx* c, const HpvKernelKey& k, long long n_points, int& block, 
         HPV_CK(hpv_dispatch(k, l));
         const size_t sm = (size_t)out;
         if (sm > 227 * 1024) continue;
+        // leave >= 12 KB of the SM's 228 KB to the L1 (register spills, Gbar / geometry reads): at C4 15 warps with
+        // 215 KB run 1 953 us, 16 warps with 229 KB 1 997 us (profiles/r02r)
+        if (sm > 216 * 1024 && w > 1 && !forced) continue;
         const long long iters = (n_wt + (long long)c->n_sm * w - 1) / ((long long)c->n_sm * w);
         if (forced ? (w == forced || !best_w) : (!best_w || iters <= best_iters)) { best_w = w; best_iters = iters; best_smem = sm; }
         if (forced && w == forced) break;
     }
     if (!best_w) return fail(c, HPV_ERR_LIMIT, "network too deep/wide for the shared-memory plan of the MLP reverse sweep");
-    // Shape of the W warps of an SM: CTAs of 4 warps when W is a multiple of 4, one CTA of W warps otherwise.
-    // Measured (profiles/r02h, r02i): the warps of one big CTA start in lockstep and convoy through the same phases
-    // (12 warps as 1 CTA 2 251 us vs 3 CTAs 2 184 us at C4; two-tangent mode 8 warps as 1 CTA 256 us vs 2 CTAs
-    // 227 us at C3); separately launched CTAs do not.  HPV_BWD_STAGGER_NS offsets the warp rows of a big CTA instead.
+    // Shape of the W warps of an SM: one CTA.  (With the 168-register build of round 2a, 4-warp CTAs were faster than
+    // one 12-warp CTA -- the warps of a big CTA start in lockstep and convoy through the phases --; with 128 registers
+    // and 15 warps the single CTA wins at C3 and C4, and several small CTAs per SM interact badly with the
+    // programmatic dependent launches (profiles/r02q, r02r).  HPV_BWD_CTA_WARPS regroups for experiments.)
     int wcta = best_w;
     int force_cta = 0;
-    if (const char* ev = getenv("HPV_BWD_CTA_WARPS")) force_cta = atoi(ev);      // tuning override: warps per CTA
+    if (const char* ev = getenv("HPV_BWD_CTA_WARPS")) force_cta = atoi(ev);
     if (force_cta > 0 && best_w % force_cta == 0) {
         l.op = 2; l.block = 32 * force_cta;
         HPV_CK(hpv_dispatch(k, l));
         wcta = force_cta; best_smem = (size_t)out;
-    } else if (best_w % 4 == 0 && best_w > 4) {
-        l.op = 2; l.block = 128;
-        HPV_CK(hpv_dispatch(k, l));
-        wcta = 4; best_smem = (size_t)out;
     }
     block = 32 * wcta; smem = best_smem;
     const long long n_grp = (n_wt + wcta - 1) / wcta;
