@@ -56,7 +56,14 @@ HPV_HD void hpv_stage_tables(const HpvCta& c, const HpvVarArgs& a, float* sm, co
         if (o_tab[t] < 0) continue;
         const float* src = a.tab[t];
         float* dst = sm + o_tab[t];
-        for (int i = c.tid * 4; i < a.Q * HPV_NP; i += c.nthreads * 4) hpv_st4(dst + i, hpv_ld4(src + i));
+        // four loads in flight per thread before the first store (the copy is latency-bound otherwise)
+        const int n = a.Q * HPV_NP, step = c.nthreads * 4;
+        int i = c.tid * 4;
+        for (; i + 3 * step < n; i += 4 * step) {
+            const HpvF4 v0 = hpv_ld4(src + i), v1 = hpv_ld4(src + i + step), v2 = hpv_ld4(src + i + 2 * step), v3 = hpv_ld4(src + i + 3 * step);
+            hpv_st4(dst + i, v0); hpv_st4(dst + i + step, v1); hpv_st4(dst + i + 2 * step, v2); hpv_st4(dst + i + 3 * step, v3);
+        }
+        for (; i < n; i += step) hpv_st4(dst + i, hpv_ld4(src + i));
     }
 }
 
@@ -151,23 +158,44 @@ HPV_HD void hpv_varfwd_body(const HpvCta& c, const HpvVarArgs& a) {
         hpv_sync(c);
 
         // (3) first contraction, over the x index:  P_t[jl][r] = c_t * sum_i G_t[jl][i] * R_t[i][r]
+        //     item = (term, group of 4 rows, group of 4 test functions): a 4x4 register tile, per i one 128-bit load of
+        //     the table row and four scalar loads of the field (16 FMAs per 5 loads; at most one round of items)
         {
-            const int nitems = a.n_terms * nrows * (HPV_NP / 4);
+            const int ng = (nrows + 3) >> 2;
+            const int nitems = a.n_terms * ng * (HPV_NP / 4);
             for (int item = tid; item < nitems; item += T) {
                 const int r4 = item & 15, rest = item >> 4;
-                const int jl = rest % nrows, t = rest / nrows;
-                const float* g = s_G + t * L.GS + jl * Q;
+                const int g4 = rest % ng, t = rest / ng;
+                const int jl0 = 4 * g4;
+                // rows beyond the chunk read row nrows-1 again (never stored)
+                const float* g0 = s_G + t * L.GS + (jl0 + 0 < nrows ? jl0 + 0 : nrows - 1) * Q;
+                const float* g1 = s_G + t * L.GS + (jl0 + 1 < nrows ? jl0 + 1 : nrows - 1) * Q;
+                const float* g2 = s_G + t * L.GS + (jl0 + 2 < nrows ? jl0 + 2 : nrows - 1) * Q;
+                const float* g3 = s_G + t * L.GS + (jl0 + 3 < nrows ? jl0 + 3 : nrows - 1) * Q;
                 const float* R = sm + L.tab[a.terms[t].rtab] + 4 * r4;
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 8
+                float acc[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+#pragma unroll 4
                 for (int i = 0; i < Q; ++i) {
-                    const float gv = g[i];
                     const HpvF4 w = hpv_ld4(R + i * HPV_NP);
-                    a0 = fmaf(gv, w.x, a0); a1 = fmaf(gv, w.y, a1); a2 = fmaf(gv, w.z, a2); a3 = fmaf(gv, w.w, a3);
+                    const float gv[4] = {g0[i], g1[i], g2[i], g3[i]};
+                    const float ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(gv[u], ws[v], acc[u][v]);
                 }
                 const float ct = hpv_term_scale(a.terms[t], hwx, hwy);
-                HpvF4 o; o.x = ct * a0; o.y = ct * a1; o.z = ct * a2; o.w = ct * a3;
-                hpv_st4(s_P + (t * L.RMAX + jl) * HPV_NP + 4 * r4, o);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (jl0 + u < nrows) {
+                        HpvF4 o; o.x = ct * acc[u][0]; o.y = ct * acc[u][1]; o.z = ct * acc[u][2]; o.w = ct * acc[u][3];
+                        hpv_st4(s_P + (t * L.RMAX + jl0 + u) * HPV_NP + 4 * r4, o);
+                    }
+                }
             }
         }
         hpv_sync(c);

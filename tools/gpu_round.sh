@@ -9,6 +9,7 @@ O=gpurun_out/$TAG
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $O/gpu.txt 2>&1
 echo "== pytest -m gpu" ; timeout 900 python -m pytest tests -m gpu -q > $O/pytest_gpu.log 2>&1; echo "pytest exit $?" | tee -a $O/pytest_gpu.log; tail -5 $O/pytest_gpu.log
+echo "== smoke"; timeout 300 python __graft_entry__.py smoke > $O/smoke.log 2>&1; tail -2 $O/smoke.log
 echo "== bench default"; timeout 600 python bench.py > $O/bench_default.json 2> $O/bench_default.err; tail -c 3000 $O/bench_default.json
 echo "== bench two-tangent sweep"; HPV_BWD_DIR=0 timeout 300 python bench.py --steps 500 --no-cpu-baseline > $O/bench_dir0.json 2> $O/bench_dir0.err
 for v in $VARIANTS; do
