@@ -342,7 +342,7 @@ int launch_mlpbwd_var(hpv_ctx* c) {
     HpvBwdArgs ba; fill_var_args(c, ba.v);
     const int rows = (c->net.dim == 2) ? c->Q : 1;
     ba.Gbar = c->Gbar.p; ba.n_points = c->n_el * rows * c->Q;
-    ba.n_tiles = (ba.n_points + c->bwd_block - 1) / c->bwd_block; ba.pts = nullptr;
+    ba.pts = nullptr;
     ba.stagger_ns = c->bwd_stagger_ns;
     HpvLaunch l; memset(&l, 0, sizeof(l));
     l.kind = HPV_K_MLPBWD; l.op = 0; l.grid = c->bwd_grid; l.block = c->bwd_block; l.smem = c->bwd_smem;
@@ -414,7 +414,7 @@ int launch_mlpbwd_points(hpv_ctx* c, PointSet& ps, int& grid_out) {
     a.terms[0] = hpv_term_zero();
     for (int f = 0; f < HPV_NFIELDS; ++f) { a.terms[0].a0[f] = ps.a0[f]; a.terms[0].a1[f] = ps.a1[f]; }
     a.grad_part = c->grad_part.p; a.grad_stride = c->grad_stride;
-    ba.Gbar = ps.gbar.p; ba.n_points = ps.n; ba.n_tiles = (ps.n + block - 1) / block; ba.pts = ps.pts.p;
+    ba.Gbar = ps.gbar.p; ba.n_points = ps.n; ba.pts = ps.pts.p;
     if ((size_t)grid * c->grad_stride > c->grad_part.n) grid = (int)(c->grad_part.n / c->grad_stride);
     HpvLaunch l; memset(&l, 0, sizeof(l));
     l.kind = HPV_K_MLPBWD; l.op = 0; l.grid = grid; l.block = block; l.smem = smem; l.stream = c->stream; l.bwd = &ba;

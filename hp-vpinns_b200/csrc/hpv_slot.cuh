@@ -53,15 +53,9 @@ HPV_HD void hpv_store_state(float* slot, int T, int tid, const HpvState<DIM, MX,
     constexpr int SP = HpvSP<HP>::value;
     hpv_each_ch<M>(s, [&](const hpv_pair* a, int c) {
         float* row = slot + ((size_t)c * T + tid) * SP;
-#if defined(HPV_STORE64) && defined(__CUDA_ARCH__)
-        // tuning variant: 64-bit stores straight from the packed pairs (no register gathering into aligned quads,
-        // but two-way bank conflicts with the row stride SP)
-#pragma unroll
-        for (int m = 0; m < HP / 2; ++m) *reinterpret_cast<unsigned long long*>(row + 2 * m) = a[m];
-#else
+        // (64-bit stores straight from the packed pairs were measured no faster: two-way bank conflicts, r02d)
 #pragma unroll
         for (int j4 = 0; j4 < HP / 4; ++j4) hpv_st_pairs(row + 4 * j4, a[2 * j4], a[2 * j4 + 1]);
-#endif
     });
 }
 

@@ -146,7 +146,6 @@ struct HpvBwdArgs {
     HpvVarArgs v;
     const float* Gbar;         // [term][n_points]  (n_points = n_el*rows*Q for the variational loss)
     int n_points;
-    int n_tiles;               // tiles of blockDim points
     // scattered-point mode (boundary / PINN losses): coordinates and per-point adjoints are given directly
     const float* pts;          // [n][dim] or null (then the points are the element quadrature points)
     int stagger_ns;            // start delay per warp "row" (warp / 4), see hpv_mlpbwd_body

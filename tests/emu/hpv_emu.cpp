@@ -213,7 +213,7 @@ int hpv_emu_varloss(int dim, const int* layers, int n_layers, int act, int Q, co
     std::vector<float> gpart((size_t)grid_b * stride, 0.0f), gpad(stride, 0.0f);
     HpvBwdArgs ba;
     ba.v = a; ba.v.grad_part = gpart.data(); ba.v.grad_stride = stride;
-    ba.Gbar = Gbar.data(); ba.n_points = npts; ba.n_tiles = ntiles; ba.pts = nullptr;
+    ba.Gbar = Gbar.data(); ba.n_points = npts; ba.pts = nullptr; ba.stagger_ns = 0;
     r = emu_bwd(k, ba, grid_b, bwd_block);
     if (r) return r;
     reduce_grad(gpart, grid_b, stride, net.theta_pad_n + 1, gpad, 0);
@@ -270,7 +270,7 @@ int hpv_emu_points(int dim, const int* layers, int n_layers, int act, const doub
     ba.v.Q = 1; ba.v.rows = 1; ba.v.n_terms = 1; ba.v.terms[0] = hpv_term_zero();
     for (int f = 0; f < HPV_NFIELDS; ++f) { ba.v.terms[0].a0[f] = a.a0[f]; ba.v.terms[0].a1[f] = a.a1[f]; }
     ba.v.grad_part = gpart.data(); ba.v.grad_stride = stride;
-    ba.Gbar = gbar.data(); ba.n_points = n; ba.n_tiles = ntiles; ba.pts = p.data();
+    ba.Gbar = gbar.data(); ba.n_points = n; ba.pts = p.data();
     r = emu_bwd(k, ba, grid_b, bwd_block);
     if (r) return r;
     reduce_grad(gpart, grid_b, stride, net.theta_pad_n + 1, gpad, 0);
