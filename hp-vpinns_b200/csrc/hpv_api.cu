@@ -92,6 +92,7 @@ struct hpv_ctx {
     std::vector<double> host_f64;
     // pinned staging of hpv_set_params (no host synchronisation: the copies are asynchronous and the buffer is
     // only rewritten after `param_staged` says the previous upload has been consumed)
+    DevBuf<unsigned char> param_blob;                 // device side of the staged upload (scattered by a kernel)
     unsigned char* param_stage = nullptr; size_t param_stage_bytes = 0;
     cudaEvent_t param_staged = nullptr; bool param_stage_busy = false;
     // constant-memory mirrors of theta_pad, one per kernel translation unit kind (forward, reverse sweep, points)
@@ -500,6 +501,7 @@ void hpv_destroy(hpv_ctx* c) {
         c->ps[s].pts.release(); c->ps[s].target.release(); c->ps[s].resid.release(); c->ps[s].gbar.release();
         c->ps[s].blk_loss.release();
     }
+    c->param_blob.release();
     if (c->param_stage) cudaFreeHost(c->param_stage);
     if (c->param_staged) cudaEventDestroy(c->param_staged);
     for (void* q : c->peer_opened) cudaIpcCloseMemHandle(q);
@@ -545,7 +547,7 @@ int hpv_set_network(hpv_ctx* c, int dim, const int* layers, int n_layers, int ac
     HPV_CK(c->eps.alloc(1));
     HPV_CK(cudaMemsetAsync(c->eps.p, 0, sizeof(float), c->stream));
     HPV_CK(c->master.alloc(P + 1)); HPV_CK(c->adam_m.alloc(P + 1)); HPV_CK(c->adam_v.alloc(P + 1));
-    HPV_CK(c->grad_out.alloc(P + 1));
+    HPV_CK(c->grad_out.alloc(P + 1 + 8));
     HPV_CK(cudaMemsetAsync(c->master.p, 0, (P + 1) * sizeof(double), c->stream));
     HPV_CK(c->adam_clock.alloc(6));
     { int r = upload(c, c->pad_index, net.pad_index); if (r) return r; }
@@ -585,12 +587,26 @@ int hpv_set_params(hpv_ctx* c, const double* theta, int n, double eps) {
     double* sm = reinterpret_cast<double*>(c->param_stage + off_m);
     memcpy(sp, pad.data(), nb_pad);
     memcpy(sm, theta, (size_t)n * sizeof(double)); sm[n] = eps;
-    HPV_CK(cudaMemcpyAsync(c->theta_pad.p, sp, c->net.theta_pad_n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    HPV_CK(cudaMemcpyAsync(c->eps.p, sp + c->net.theta_pad_n, sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    HPV_CK(cudaMemcpyAsync(c->master.p, sm, nb_m, cudaMemcpyHostToDevice, c->stream));
+    // one host-to-device copy of the blob, one kernel that scatters it into the parameter buffers and into the
+    // constant-memory mirrors this context owns (instead of three copies now and one re-staging copy per mirror later)
+    if (c->param_blob.n < off_m + nb_m) HPV_CK(c->param_blob.alloc(off_m + nb_m));
+    HPV_CK(cudaMemcpyAsync(c->param_blob.p, c->param_stage, off_m + nb_m, cudaMemcpyHostToDevice, c->stream));
     HPV_CK(cudaEventRecord(c->param_staged, c->stream));
     c->param_stage_busy = true;
-    theta_changed(c);
+    HpvParamScatterArgs pa; memset(&pa, 0, sizeof(pa));
+    pa.blob_pad = reinterpret_cast<const float*>(c->param_blob.p);
+    pa.blob_master = reinterpret_cast<const double*>(c->param_blob.p + off_m);
+    pa.theta_pad_n = c->net.theta_pad_n; pa.n_master = n + 1;
+    pa.theta_pad = c->theta_pad.p; pa.eps = c->eps.p; pa.master = c->master.p;
+    bool wrote[3] = {false, false, false};
+    if (c->adam_direct) {
+        std::lock_guard<std::mutex> lock(g_owner_mutex);
+        const int hpi = c->net.hp == 8 ? 0 : (c->net.hp == 20 ? 1 : 2);
+        for (int k = 0; k < 3; ++k)
+            if (c->mirror[k] && g_owner[c->device & 15][hpi][k] == c) { pa.mirror[k] = c->mirror[k]; wrote[k] = true; }
+    }
+    HPV_CK(hpv_launch_param_scatter(pa, c->stream));
+    for (int k = 0; k < 3; ++k) c->mirror_stale[k] = !wrote[k];      // a written mirror now holds the complete new set
     return HPV_OK;
 }
 
@@ -1031,17 +1047,22 @@ int hpv_read_losses_and_grad(hpv_ctx* c, double* losses, int nl, double* g, int 
     if (!losses || nl < 1 || !g || n != c->net.n_theta) return fail(c, HPV_ERR_ARG, "bad output buffers");
     if (!c->redbuf.p) return fail(c, HPV_ERR_STATE, "hpv_loss_and_grad has not been called");
     HPV_CK(cudaSetDevice(c->device));
-    { int r = unpad_grad(c, 0); if (r) return r; }
+    {   // un-pad the gradient and append the loss values: one kernel, one device-to-host copy, one synchronisation
+        HpvAdamArgs a;
+        bool wrote[3];
+        fill_adam_args(c, a, 0, wrote);
+        a.losses_in = c->redbuf.p + c->loss_off;
+        HPV_CK(hpv_launch_adam(a, c->stream));
+        c->launches += 1;
+    }
     std::vector<double>& gh = c->host_f64;
-    gh.resize(n + 1);
-    float h[8];
-    HPV_CK(cudaMemcpyAsync(gh.data(), c->grad_out.p, (n + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    HPV_CK(cudaMemcpyAsync(h, c->redbuf.p + c->loss_off, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-    HPV_CK(cudaStreamSynchronize(c->stream));                      // the one host synchronisation of the step
+    gh.resize(n + 1 + 8);
+    HPV_CK(cudaMemcpyAsync(gh.data(), c->grad_out.p, (n + 1 + 8) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    HPV_CK(cudaStreamSynchronize(c->stream));
     { int r = check_peer_error(c); if (r) return r; }
     memcpy(g, gh.data(), n * sizeof(double));
     if (ge) *ge = gh[n];
-    for (int i = 0; i < nl && i < 8; ++i) losses[i] = h[i];
+    for (int i = 0; i < nl && i < 8; ++i) losses[i] = gh[n + 1 + i];
     return HPV_OK;
 }
 

@@ -163,6 +163,7 @@ cudaError_t hpv_launch_gradreduce(const HpvGradReduceArgs& a, const HpvLossArgs*
 // Stand-alone form (after the NCCL all-reduce of the multi-GPU step, and to un-pad a gradient for the host):
 // one CTA, thread-strided over the parameters (reference order, eps last).
 __global__ void __launch_bounds__(1024) hpv_adam_kernel(const HpvAdamArgs a) {
+    if (a.losses_in && a.grad_out && threadIdx.x < 8) a.grad_out[a.n_theta + 1 + threadIdx.x] = (double)a.losses_in[threadIdx.x];
     const double lr_t = hpv_adam_clock(a, threadIdx.x == 0);
     for (int r = threadIdx.x; r <= a.n_theta; r += blockDim.x) {
         const double g = (double)(r == a.n_theta ? a.grad_pad[a.theta_pad_n] : a.grad_pad[a.pad_index[r]]);
@@ -175,6 +176,24 @@ cudaError_t hpv_launch_adam(const HpvAdamArgs& a, cudaStream_t s) {
     int block = ((n + 31) / 32) * 32;
     if (block > 1024) block = 1024;
     hpv_adam_kernel<<<1, block, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) hpv_param_scatter_kernel(const HpvParamScatterArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.theta_pad_n) {
+        const float v = a.blob_pad[i];
+        a.theta_pad[i] = v;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) if (a.mirror[k]) a.mirror[k][i] = v;
+    }
+    if (i == 0) a.eps[0] = a.blob_pad[a.theta_pad_n];
+    if (i < a.n_master) a.master[i] = a.blob_master[i];
+}
+
+cudaError_t hpv_launch_param_scatter(const HpvParamScatterArgs& a, cudaStream_t s) {
+    const int n = a.theta_pad_n > a.n_master ? a.theta_pad_n : a.n_master;
+    hpv_param_scatter_kernel<<<(n + 255) / 256, 256, 0, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -135,7 +135,8 @@ struct HpvAdamArgs {
     float* mirror[3];          // constant-memory mirrors of theta_pad this context currently owns (or null): the
                                // update is written into them directly, saving the device-to-device re-staging copies
     float* eps;                // device scalar read by the kernels
-    double* grad_out;          // [n_theta + 1] unpadded gradient or null
+    double* grad_out;          // [n_theta + 1 + 8] unpadded gradient (or null), followed by the loss values
+    const float* losses_in;    // [8] loss values to append to grad_out (or null): one device-to-host copy returns both
     int train_eps;
     double lr, b1, b2, eps_hat;
     const int* ref_index;      // [theta_pad_n + 1] padded index -> reference-order index (eps: n_theta), -1: none
@@ -146,4 +147,14 @@ struct HpvAdamArgs {
     int update;                // 0: only unpad the gradient, 1: also apply the Adam update
 };
 cudaError_t hpv_launch_adam(const HpvAdamArgs& a, cudaStream_t s);
+// hpv_set_params on the device: one staged blob [theta_pad | eps | (8-byte aligned) master] is scattered into the
+// parameter buffers and the constant-memory mirrors the context owns (no separate copies per destination).
+struct HpvParamScatterArgs {
+    const float* blob_pad;     // [theta_pad_n] padded fp32 parameters, followed by eps
+    const double* blob_master; // [n_master] float64 master copy (reference order, eps last)
+    int theta_pad_n, n_master;
+    float* theta_pad; float* eps; double* master;
+    float* mirror[3];
+};
+cudaError_t hpv_launch_param_scatter(const HpvParamScatterArgs& a, cudaStream_t s);
 cudaError_t hpv_launch_ffma_peak(float* out, int grid, int block, int iters, int variant, cudaStream_t s);
