@@ -78,6 +78,7 @@ int g_bwd_dir = 1;      // as hpv_ctx::bwd_dir: allow the directional reverse sw
 #define EMU_DISPATCH(CALL)                                                          \
     if (k.hp == 8) { EMU_MODE(8, CALL) }                                            \
     else if (k.hp == 20) { EMU_MODE(20, CALL) }                                     \
+    else if (k.hp == 32) { EMU_MODE(32, CALL) }                                     \
     else return -4;
 
 int emu_fwd(const Key& k, const HpvVarArgs& a, int grid, size_t smem) {
@@ -100,6 +101,7 @@ int emu_bwd(const Key& k, const HpvBwdArgs& a, int grid, int block) {
         if (dir) {
             if (k.hp == 8) { EMU_ACT(2, 1, 0, 8, CALL) }
             else if (k.hp == 20) { EMU_ACT(2, 1, 0, 20, CALL) }
+            else if (k.hp == 32) { EMU_ACT(2, 1, 0, 32, CALL) }
             else return -4;
             return 0;
         }

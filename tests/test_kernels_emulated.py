@@ -49,6 +49,30 @@ def test_directional_reverse_sweep_matches_two_tangent_sweep(name):
     assert np.abs(out[0] - out[1]).max() <= 2e-5 * np.abs(gref).max()      # ... one gradient
 
 
+@pytest.mark.parametrize("layers,var_form", [([2, 27, 31, 1], 1), ([2, 32, 32, 1], 0)])
+def test_padded_width_32_on_emulated_kernels(layers, var_form):
+    """Hidden width padded to 32: the weight-gradient GEMM has more register tiles (72) than a warp has lanes and
+    walks them in batches; unequal widths exercise the zero padding.  var_form 1 takes the directional sweep,
+    var_form 0 the five-channel one."""
+    rng = np.random.default_rng(11)
+    Q, N = 8, 4
+    X, W = O.GaussLobattoJacobiWeights(Q, 0, 0)
+    gx, gy = np.array([-1.0, 0.1, 1.0]), np.array([-1.0, 1.0])
+    F = O.rhs_2d_factorised(gx, gy, N, N, X, W)
+    Ws, bs = O.xavier_params(layers, 4)
+    bs = [0.1 * rng.standard_normal(b.shape) for b in bs]
+    theta = O.pack_theta(Ws, bs)
+    lo = np.array([[gx[i], gy[0]] for i in range(2)])
+    hi = np.array([[gx[i + 1], gy[1]] for i in range(2)])
+    D1, D2 = O.dTest_fcn(N, X)
+    kw = dict(problem="poisson2d", var_form=var_form, layers=layers, act="tanh", xi=X, w=W, T=O.Test_fcn(N, X), D1=D1, D2=D2,
+              d1b=None, lo=lo, hi=hi, ntx=N, nty=N, F=F.reshape(2, N, N), theta=theta)
+    l_ref, g_ref = O.loss_and_grad(lambda Wt, bt: O.varloss_2d_factorised(Wt, bt, X, W, F, gx, gy, N, N, var_form)[0], Ws, bs)
+    loss, res, el, g, _ = E.varloss(n_ctas_fwd=2, n_ctas_bwd=2, bwd_block=64, **kw)
+    assert loss == pytest.approx(float(l_ref), rel=1e-5)
+    assert np.abs(g - g_ref).max() <= 1e-4 * np.abs(g_ref).max()
+
+
 def test_partition_independence_and_determinism():
     """Same numbers whatever the number of CTAs an element is split over (fixed-order reductions)."""
     c = C.load("p2d_vf1_w20")          # Q = 12 -> 144 points per element -> one tile per element
