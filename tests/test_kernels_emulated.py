@@ -73,6 +73,25 @@ def test_padded_width_32_on_emulated_kernels(layers, var_form):
     assert np.abs(g - g_ref).max() <= 1e-4 * np.abs(g_ref).max()
 
 
+@pytest.mark.parametrize("bwd_block", [32, 96, 160])
+def test_reverse_sweep_block_shapes(bwd_block):
+    """The reverse sweep is launched as one CTA of W warps per SM, W chosen per launch (1 warp for a handful of
+    boundary points, 11-15 for the element batch): any number of warps, including non-powers of two, must give the
+    same gradient (the CTA-wide sums and the trip count of the tile groups depend on it)."""
+    c = C.load("p2d_vf1_w20")
+    inp = C.engine_inputs(c)
+    gref = C.oracle_lossv(c)[2]
+    g = E.varloss(n_ctas_fwd=2, n_ctas_bwd=2, bwd_block=bwd_block, **inp)[3]
+    assert np.abs(g - gref).max() <= 1e-4 * np.abs(gref).max()
+    xb, ub = c["X_u_train"], c["u_train"]
+    Ws, bs = O.unpack_theta(c["theta"], c["layers"])
+    lref, gref = O.loss_and_grad(lambda W, b: 10 * O.lossb(W, b, xb, ub, "tanh"), Ws, bs)
+    _, _, _, lb, g, _ = E.points(c["layers"], "tanh", c["theta"], xb, target=ub.ravel(), a0=[1, 0, 0, 0, 0], weight=10.0, mode=0,
+                                 backward=True, bwd_block=bwd_block)
+    assert lb == pytest.approx(lref, rel=1e-5)
+    assert np.abs(g - gref).max() <= 1e-4 * np.abs(gref).max()
+
+
 def test_partition_independence_and_determinism():
     """Same numbers whatever the number of CTAs an element is split over (fixed-order reductions)."""
     c = C.load("p2d_vf1_w20")          # Q = 12 -> 144 points per element -> one tile per element
