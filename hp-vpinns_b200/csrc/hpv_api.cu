@@ -224,7 +224,7 @@ int plan_bwd(hpv_ctx* c, const HpvKernelKey& k, long long n_points, int& block, 
         if (forced && w == forced) break;
     }
     if (!best_w) return fail(c, HPV_ERR_LIMIT, "network too deep/wide for the shared-memory plan of the MLP reverse sweep");
-    // Shape of the W warps of an SM: one CTA.  (With the 168-register build of round 2a, 4-warp CTAs were faster than
+    // Shape of the W warps of an SM: one CTA.  (With the earlier 168-register build, 4-warp CTAs were faster than
     // one 12-warp CTA -- the warps of a big CTA start in lockstep and convoy through the phases --; with 128 registers
     // and 15 warps the single CTA wins at C3 and C4, and several small CTAs per SM interact badly with the
     // programmatic dependent launches (profiles/r02q, r02r).  HPV_BWD_CTA_WARPS regroups for experiments.)
