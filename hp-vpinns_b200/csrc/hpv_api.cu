@@ -63,6 +63,7 @@ struct hpv_ctx {
     DevBuf<unsigned> peer_flags_own, peer_err;
     int peer_n = 0, peer_rank = 0, peer_nvp = 0, peer_nchunks = 0;
     unsigned peer_seq = 0;
+    unsigned long long peer_timeout_ns = 20000000000ull;     // HPV_PEER_TIMEOUT_S: how long a rank waits for its peers
     float* peer_inbox[HPV_MAX_PEERS] = {nullptr};
     unsigned* peer_flags[HPV_MAX_PEERS] = {nullptr};
     std::vector<void*> peer_opened;
@@ -364,7 +365,7 @@ int launch_gradreduce(hpv_ctx* c, int n_parts, int accumulate, const HpvLossArgs
         memset(&pa, 0, sizeof(pa));
         pa.nranks = c->peer_n; pa.rank = c->peer_rank; pa.seq = ++c->peer_seq; pa.nvp = c->peer_nvp; pa.nchunks = c->peer_nchunks;
         for (int r = 0; r < c->peer_n; ++r) { pa.inbox[r] = c->peer_inbox[r]; pa.flags[r] = c->peer_flags[r]; }
-        pa.err = c->peer_err.p; pa.timeout_ns = 5000000000ull;
+        pa.err = c->peer_err.p; pa.timeout_ns = c->peer_timeout_ns;
     }
     HPV_CK(hpv_launch_gradreduce(g, la, adam, exchange ? &pa : nullptr, c->loss_off, c->stream));
     c->launches += 1;
@@ -433,7 +434,7 @@ int check_peer_error(hpv_ctx* c) {
     if (!c->peer_n) return HPV_OK;
     unsigned e = 0;
     HPV_CK(cudaMemcpy(&e, c->peer_err.p, sizeof(e), cudaMemcpyDeviceToHost));
-    if (e) return fail(c, HPV_ERR_CUDA, "peer gradient exchange timed out (5 s): a rank of the node did not arrive");
+    if (e) return fail(c, HPV_ERR_CUDA, "peer gradient exchange timed out (HPV_PEER_TIMEOUT_S, default 20 s): a rank of the node did not arrive");
     return HPV_OK;
 }
 
@@ -477,6 +478,7 @@ int hpv_create(hpv_ctx** out, int device) {
     if (const char* ev = getenv("HPV_BWD_DIR")) ctx->bwd_dir = atoi(ev) != 0;
     if (const char* ev = getenv("HPV_ADAM_DIRECT")) ctx->adam_direct = atoi(ev) != 0;
     if (const char* ev = getenv("HPV_BWD_STAGGER_NS")) ctx->bwd_stagger_ns = atoi(ev);
+    if (const char* ev = getenv("HPV_PEER_TIMEOUT_S")) { const double v = atof(ev); if (v > 0) ctx->peer_timeout_ns = (unsigned long long)(v * 1e9); }
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete ctx;

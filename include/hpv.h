@@ -120,7 +120,7 @@ int hpv_adam_step(hpv_ctx* ctx);
  *   hpv_peer_export  : allocates this rank's inbox + flags, returns their two CUDA IPC handles (128 bytes).
  *   hpv_peer_connect : all_handles = the nranks x 128 bytes gathered from every rank (rank order).
  * Without a connection the caller all-reduces hpv_reduce_buffer itself (NCCL) between hpv_loss_and_grad and
- * hpv_adam_step.  A rank that fails to arrive within 5 s makes the others report an error instead of hanging. */
+ * hpv_adam_step.  A rank that fails to arrive within 20 s (HPV_PEER_TIMEOUT_S) makes the others report an error instead of hanging. */
 int hpv_peer_export(hpv_ctx* ctx, int nranks, unsigned char* handles_128_bytes);
 int hpv_peer_connect(hpv_ctx* ctx, int rank, int nranks, const unsigned char* all_handles);
 int hpv_read_losses(hpv_ctx* ctx, double* out, int n);
