@@ -131,6 +131,25 @@ extern "C" {
 
 void hpv_emu_set_bwd_dir(int on) { g_bwd_dir = on; }
 
+// Host-side planning helpers exposed for property tests.
+// hpv_partition: returns n_ctas; cta_tile_begin [n_ctas+1], el_first_cta / el_nparts / el_part_off [n_el].
+int hpv_emu_partition(int n_el, int pts_per_el, int tile_pts, int max_ctas, int cta_pts, int* tiles_per_el, int* total_parts,
+                      int* cta_tile_begin, int* el_first_cta, int* el_nparts, int* el_part_off) {
+    HpvPartition p;
+    hpv_partition(p, n_el, pts_per_el, tile_pts, max_ctas, cta_pts);
+    *tiles_per_el = p.tiles_per_el; *total_parts = p.total_parts;
+    for (int c = 0; c <= p.n_ctas; ++c) cta_tile_begin[c] = p.cta_tile_begin[c];
+    for (int e = 0; e < n_el; ++e) { el_first_cta[e] = p.el_first_cta[e]; el_nparts[e] = p.el_nparts[e]; el_part_off[e] = p.el_part_off[e]; }
+    return p.n_ctas;
+}
+
+// padded parameter index -> compact gradient index of the reverse sweep (or -1), and the compact length
+int hpv_emu_gw_of_padded(int dim, int hp, int nhid, int ip) { return hpv_gw_of_padded(dim, hp, nhid, ip); }
+int hpv_emu_gw_n(int dim, int hp, int nhid) { return hpv_gw_n(dim, hp, nhid); }
+int hpv_emu_theta_pad_n(int dim, int hp, int nhid) { return hpv_theta_pad_n(dim, hp, nhid); }
+int hpv_emu_off_wt(int dim, int hp, int l) { return hpv_off_wt(dim, hp, l); }
+int hpv_emu_off_wl(int dim, int hp, int l) { return hpv_off_wl(dim, hp, l); }
+
 // Variational loss forward (+ backward when grad_theta != NULL) on emulated CTAs.
 //   n_ctas_fwd / n_ctas_bwd / bwd_block choose the launch geometry (to exercise the split-element paths).
 int hpv_emu_varloss(int dim, const int* layers, int n_layers, int act, int Q, const double* xi, const double* w,
