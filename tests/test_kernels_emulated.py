@@ -92,6 +92,20 @@ def test_reverse_sweep_block_shapes(bwd_block):
     assert np.abs(g - gref).max() <= 1e-4 * np.abs(gref).max()
 
 
+@pytest.mark.parametrize("name", ["c1", "c2", "c5"])
+def test_baseline_configs_at_full_size_on_emulated_kernels(name):
+    """C1, C2 and C5 of BASELINE.json at their full sizes (Q = 50 / 80, up to 60 x 60 test functions) through the kernel
+    bodies on host threads; the GPU twin is tests/test_gpu_zz_baseline_configs.py."""
+    from tests import _baseline_cases as B
+    inp, l_ref, g_ref, r_ref, ge_ref = B.build(name)
+    loss, res, el, g, ge = E.varloss(n_ctas_fwd=8, n_ctas_bwd=8, bwd_block=128, **inp)
+    assert loss == pytest.approx(l_ref, rel=1e-5)
+    assert np.abs(res - r_ref.reshape(res.shape)).max() <= 2e-5 * np.abs(r_ref).max()
+    assert np.abs(g - g_ref).max() <= 1e-4 * np.abs(g_ref).max()
+    if ge_ref is not None:
+        assert ge == pytest.approx(ge_ref, rel=1e-4)
+
+
 def test_partition_independence_and_determinism():
     """Same numbers whatever the number of CTAs an element is split over (fixed-order reductions)."""
     c = C.load("p2d_vf1_w20")          # Q = 12 -> 144 points per element -> one tile per element
