@@ -31,6 +31,15 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+// Scope guard for the temporary device buffers of a single call: released on every return path (HPV_CK returns early).
+template <typename T>
+struct ScopedBuf : DevBuf<T> {
+    ScopedBuf() = default;
+    ScopedBuf(const ScopedBuf&) = delete;
+    ScopedBuf& operator=(const ScopedBuf&) = delete;
+    ~ScopedBuf() { this->release(); }
+};
+
 struct PointSet {
     bool active = false;
     int n = 0, mx = 0, my = 0, n_ctas = 0;
@@ -53,6 +62,7 @@ struct hpv_ctx {
     int problem = -1, var_form = -1; double V = 1.0; HpvForm form; bool have_form = false;
     int n_el = 0, ntx = 0, nty = 0; bool have_el = false, has_F = false;
     bool ready = false;
+    bool grad_ready = false;           // network-dependent reduction buffers (grad_part, redbuf) match the current network
 
     // parameters / optimiser
     DevBuf<float> theta_pad, eps;
@@ -84,6 +94,18 @@ struct hpv_ctx {
     bool bwd_dir = true;               // allow the directional reverse sweep (HPV_BWD_DIR=0 disables)
     int bwd_stagger_ns = 0;            // start offset between the warp rows of the reverse sweep (HPV_BWD_STAGGER_NS)
     bool adam_direct = true;           // Adam writes the constant-memory mirrors in place (HPV_ADAM_DIRECT=0 disables)
+    // training steps replayed from a CUDA graph (hpv_train_steps): two consecutive steps are captured once per
+    // configuration (the optimizer clock is double-buffered, so the launch arguments have period 2) and re-launched
+    bool use_graph = true;             // HPV_GRAPH=0: plain launches
+    cudaGraphExec_t step_graph[2] = {nullptr, nullptr};   // one step each, for the two parities of the optimizer clock
+    unsigned long long epoch = 1, graph_epoch = 0;     // every call that changes a launch argument bumps `epoch`
+    unsigned long long plain_epoch = 0; int plain_steps = 0;   // plain steps run since the last change (lazy set-up done?)
+    int graph_launches = 0; unsigned graph_kinds = 0, used_kinds = 0; bool graph_hist = false, capturing = false;
+    bool last_wrote[3] = {false, false, false}, graph_wrote[3] = {false, false, false};   // mirrors the (captured) Adam launch writes
+    DevBuf<float> hist_ring; DevBuf<double> hist_t0;   // device-side loss history of graph-replayed steps
+    double adam_t = 0.0;                               // host copy of the optimizer's step counter
+    bool fwd_tc = true;                // forward kernel in its tensor-core form (HPV_FWD_TC=0: the FP32-FFMA form)
+    bool fwd_tc_active = false;        // ... and the current network / form / rule admit it (decided by ensure_ready)
     int fwd_ctas_per_sm = 0, adj_grid = 0, slabs_per_el = 0;
     PointSet ps[HPV_MAX_POINT_SETS];
     // training configuration
@@ -144,6 +166,7 @@ HpvKernelKey bwd_key_of(const hpv_ctx* c) {
 
 // Bring the constant-memory copy of the parameters that kernels of `kind` read up to date (stream-ordered).
 int refresh_mirror(hpv_ctx* c, int kind) {
+    c->used_kinds |= 1u << kind;
     if (!c->mirror[kind]) {
         HpvLaunch l; memset(&l, 0, sizeof(l));
         long long out = 0;
@@ -244,6 +267,23 @@ int plan_bwd(hpv_ctx* c, const HpvKernelKey& k, long long n_points, int& block, 
     return HPV_OK;
 }
 
+// Buffers of the gradient reduction.  They depend on the network only (padded parameter count), so that a step
+// made of point-wise losses alone (wv = 0) needs no element batch; hpv_set_network invalidates them.
+int ensure_grad_buffers(hpv_ctx* c, int min_parts) {
+    if (!c->grad_ready) {
+        c->grad_stride = hpv_align4(c->net.theta_pad_n + 1);
+        c->loss_off = ((c->net.theta_pad_n + 1 + 31) / 32) * 32;       // the losses start a 32-entry chunk of their own
+        HPV_CK(c->redbuf.alloc(c->loss_off + 32));
+        HPV_CK(cudaMemsetAsync(c->redbuf.p, 0, (c->loss_off + 32) * sizeof(float), c->stream));
+        c->grad_part.release();
+    }
+    int parts = min_parts;
+    if (parts < c->n_sm * 4) parts = c->n_sm * 4;                      // point-loss launches reuse the buffer
+    if (!c->grad_part.p || c->grad_part.n < (size_t)parts * c->grad_stride) HPV_CK(c->grad_part.alloc((size_t)parts * c->grad_stride));
+    c->grad_ready = true;
+    return HPV_OK;
+}
+
 int ensure_ready(hpv_ctx* c) {
     if (c->ready) return HPV_OK;
     if (!c->have_net) return fail(c, HPV_ERR_STATE, "hpv_set_network has not been called");
@@ -272,13 +312,25 @@ int ensure_ready(hpv_ctx* c) {
     for (int q = 0; q < c->Q; ++q) xi1[q] = (float)(c->xi[q] + 1.0);
     { int r = upload(c, c->xi1, xi1); if (r) return r; }
 
-    // forward launch plan
+    // forward launch plan: the tensor-core form (hpv_varfwd_tc.cuh) when its TMEM / shared-memory plan fits, else FFMA
     HpvVarArgs a; fill_var_args(c, a);
     const HpvKernelKey k = key_of(c, c->form.mx, c->form.my);
-    const HpvFwdSmem fs = hpv_fwd_smem(a, hpv_slot_floats(k.dim, k.mx, k.my, k.hp, HPV_THREADS));
-    c->fwd_smem = (size_t)fs.total * 4;
-    if (c->fwd_smem > 227 * 1024) return fail(c, HPV_ERR_LIMIT, "forward kernel shared-memory plan exceeds 227 KB (reduce Q)");
-    {
+    const int nch = hpv_mode_nch(k.dim, k.mx, k.my);
+    c->fwd_tc_active = false;
+    if (c->fwd_tc && hpv_tc_supported(nch, k.hp)) {
+        const size_t sm_tc = (size_t)hpv_fwd_tc_smem(a, k.dim, k.hp, nch).total * 4;
+        if (sm_tc <= 227 * 1024) {
+            HpvLaunch l; memset(&l, 0, sizeof(l));
+            long long out = 0;
+            l.kind = HPV_K_VARFWD_TC; l.op = 1; l.block = HPV_THREADS; l.smem = sm_tc; l.out = &out;
+            HPV_CK(hpv_dispatch(k, l));
+            if (out >= 1) { c->fwd_tc_active = true; c->fwd_smem = sm_tc; c->fwd_ctas_per_sm = (int)out; }
+        }
+    }
+    if (!c->fwd_tc_active) {
+        const HpvFwdSmem fs = hpv_fwd_smem(a, hpv_slot_floats(k.dim, k.mx, k.my, k.hp, HPV_THREADS));
+        c->fwd_smem = (size_t)fs.total * 4;
+        if (c->fwd_smem > 227 * 1024) return fail(c, HPV_ERR_LIMIT, "forward kernel shared-memory plan exceeds 227 KB (reduce Q)");
         HpvLaunch l; memset(&l, 0, sizeof(l));
         long long out = 0;
         l.kind = HPV_K_VARFWD; l.op = 1; l.block = HPV_THREADS; l.smem = c->fwd_smem; l.out = &out;
@@ -304,27 +356,22 @@ int ensure_ready(hpv_ctx* c) {
     const long long npts = (long long)c->n_el * rows * c->Q;
     { int r = plan_bwd(c, bwd_key_of(c), npts, c->bwd_block, c->bwd_grid, c->bwd_smem); if (r) return r; }
     c->bwd_ctas_per_sm = (c->bwd_grid + c->n_sm - 1) / c->n_sm;
-    c->grad_stride = hpv_align4(c->net.theta_pad_n + 1);
-    int max_grid = c->bwd_grid;
-    if (max_grid < c->n_sm * 4) max_grid = c->n_sm * 4;          // point-loss launches reuse the buffer
-    HPV_CK(c->grad_part.alloc((size_t)max_grid * c->grad_stride));
+    { int r = ensure_grad_buffers(c, c->bwd_grid); if (r) return r; }
     HPV_CK(c->Gbar.alloc((size_t)c->form.n_terms * npts));
     c->slabs_per_el = (rows + HPV_ADJ_RS - 1) / HPV_ADJ_RS;
     c->adj_grid = c->n_el * c->slabs_per_el;
     c->adj_smem = (size_t)hpv_adj_smem(a).total * 4;
     if (c->adj_smem > 227 * 1024) return fail(c, HPV_ERR_LIMIT, "adjoint projection shared-memory plan exceeds 227 KB");
-    c->loss_off = ((c->net.theta_pad_n + 1 + 31) / 32) * 32;       // the losses start a 32-entry chunk of their own
-    HPV_CK(c->redbuf.alloc(c->loss_off + 32));
-    HPV_CK(cudaMemsetAsync(c->redbuf.p, 0, (c->loss_off + 32) * sizeof(float), c->stream));
     c->ready = true;
     return HPV_OK;
 }
 
 int launch_forward(hpv_ctx* c) {
-    { int r = refresh_mirror(c, HPV_K_VARFWD); if (r) return r; }
+    // the tensor-core form reads the parameters from global memory (theta_pad), not from the constant-memory mirror
+    if (!c->fwd_tc_active) { int r = refresh_mirror(c, HPV_K_VARFWD); if (r) return r; }
     HpvVarArgs a; fill_var_args(c, a);
     HpvLaunch l; memset(&l, 0, sizeof(l));
-    l.kind = HPV_K_VARFWD; l.op = 0; l.grid = c->part.n_ctas; l.block = HPV_THREADS; l.smem = c->fwd_smem;
+    l.kind = c->fwd_tc_active ? HPV_K_VARFWD_TC : HPV_K_VARFWD; l.op = 0; l.grid = c->part.n_ctas; l.block = HPV_THREADS; l.smem = c->fwd_smem;
     l.stream = c->stream; l.var = &a;
     HPV_CK(hpv_dispatch(key_of(c, c->form.mx, c->form.my), l));
     c->launches += 1;
@@ -467,6 +514,7 @@ int hpv_create(hpv_ctx** out, int device) {
         return fail(c, HPV_ERR_CUDA, "no CUDA device: libhpv has no CPU path");
     }
     if (device < 0 || device >= n) return fail(c, HPV_ERR_ARG, "device index out of range");
+    if (device >= 16) return fail(c, HPV_ERR_LIMIT, "device index >= 16 (the per-device launch caches hold 16 entries)");
     e = cudaSetDevice(device);
     if (e != cudaSuccess) return fail(c, HPV_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
     cudaDeviceProp prop;
@@ -477,6 +525,8 @@ int hpv_create(hpv_ctx** out, int device) {
     ctx->device = device; ctx->n_sm = prop.multiProcessorCount;
     if (const char* ev = getenv("HPV_BWD_DIR")) ctx->bwd_dir = atoi(ev) != 0;
     if (const char* ev = getenv("HPV_ADAM_DIRECT")) ctx->adam_direct = atoi(ev) != 0;
+    if (const char* ev = getenv("HPV_FWD_TC")) ctx->fwd_tc = atoi(ev) != 0;
+    if (const char* ev = getenv("HPV_GRAPH")) ctx->use_graph = atoi(ev) != 0;
     if (const char* ev = getenv("HPV_BWD_STAGGER_NS")) ctx->bwd_stagger_ns = atoi(ev);
     if (const char* ev = getenv("HPV_PEER_TIMEOUT_S")) { const double v = atof(ev); if (v > 0) ctx->peer_timeout_ns = (unsigned long long)(v * 1e9); }
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
@@ -504,6 +554,8 @@ void hpv_destroy(hpv_ctx* c) {
         c->ps[s].blk_loss.release();
     }
     c->param_blob.release();
+    for (int i = 0; i < 2; ++i) if (c->step_graph[i]) cudaGraphExecDestroy(c->step_graph[i]);
+    c->hist_ring.release(); c->hist_t0.release();
     if (c->param_stage) cudaFreeHost(c->param_stage);
     if (c->param_staged) cudaEventDestroy(c->param_staged);
     for (void* q : c->peer_opened) cudaIpcCloseMemHandle(q);
@@ -523,6 +575,7 @@ int hpv_set_stream(hpv_ctx* c, void* s) {
     HPV_CK(cudaSetDevice(c->device));
     HPV_CK(cudaStreamSynchronize(c->stream));
     c->stream = s ? (cudaStream_t)s : c->own_stream;
+    c->epoch++;
     return HPV_OK;
 }
 
@@ -540,7 +593,10 @@ int hpv_set_network(hpv_ctx* c, int dim, const int* layers, int n_layers, int ac
     HpvNet net;
     if (!hpv_net_setup(net, dim, layers, n_layers, act, err)) return fail(c, HPV_ERR_ARG, err);
     if (net.theta_pad_n > HPV_CTHETA_MAX) return fail(c, HPV_ERR_LIMIT, "network too large for the constant-memory parameter mirror (12288 padded floats incl. transposed copies)");
-    c->net = net; c->have_net = true; c->ready = false;
+    if (c->peer_n || c->peer_inbox_own.p)
+        return fail(c, HPV_ERR_STATE, "hpv_set_network after hpv_peer_export: the peer exchange buffers are sized for the network they were exported with");
+    HPV_CK(cudaStreamSynchronize(c->stream));                        // nothing in flight may still use the old buffers
+    c->net = net; c->have_net = true; c->ready = false; c->epoch++; c->grad_ready = false;
     c->mirror[0] = c->mirror[1] = c->mirror[2] = nullptr;
     theta_changed(c);
     const int P = net.n_theta;
@@ -629,7 +685,7 @@ int hpv_set_quadrature(hpv_ctx* c, int Q, const double* xi, const double* w) {
     if (!c || !xi || !w) return fail(c, HPV_ERR_ARG, "NULL argument");
     if (Q < 2 || Q > HPV_QMAX) return fail(c, HPV_ERR_LIMIT, "Q must be in [2, 128]");
     c->Q = Q; c->xi.assign(xi, xi + Q); c->w.assign(w, w + Q);
-    c->have_quad = true; c->have_tabs = false; c->ready = false;
+    c->have_quad = true; c->have_tabs = false; c->ready = false; c->epoch++;
     return HPV_OK;
 }
 
@@ -643,7 +699,7 @@ int hpv_set_test_tables(hpv_ctx* c, int N, const double* T, const double* D1, co
     if (D2) c->D2.assign(D2, D2 + n); else c->D2.assign(n, 0.0);
     c->have_d1b = d1b != nullptr;
     if (d1b) c->d1b.assign(d1b, d1b + 2 * (size_t)N);
-    c->have_tabs = true; c->ready = false;
+    c->have_tabs = true; c->ready = false; c->epoch++;
     return HPV_OK;
 }
 
@@ -653,7 +709,7 @@ int hpv_set_form(hpv_ctx* c, int problem, int var_form, double V) {
     HpvForm fm;
     if (!hpv_form_setup(fm, problem, var_form, V, err)) return fail(c, HPV_ERR_ARG, err);
     c->form = fm; c->problem = problem; c->var_form = var_form; c->V = V;
-    c->have_form = true; c->ready = false;
+    c->have_form = true; c->ready = false; c->epoch++;
     return HPV_OK;
 }
 
@@ -694,7 +750,7 @@ int hpv_set_elements(hpv_ctx* c, int n_el, const double* lo, const double* hi, c
         for (size_t i = 0; i < nf; ++i) f[i] = (float)F_ext[i];
         int r = upload(c, c->F, f); if (r) return r;
     }
-    c->have_el = true; c->ready = false;
+    c->have_el = true; c->ready = false; c->epoch++;
     return HPV_OK;
 }
 
@@ -734,14 +790,18 @@ int hpv_project_field(hpv_ctx* c, const double* field, int ltab, int rtab, doubl
     const size_t npts = (size_t)c->n_el * rows * c->Q, nres = (size_t)c->n_el * c->nty * c->ntx;
     std::vector<float> hf(npts);
     for (size_t i = 0; i < npts; ++i) hf[i] = (float)field[i];
-    DevBuf<float> dfield;
-    HPV_CK(dfield.alloc(npts));
+    // scratch outputs: the projection must not disturb Res / el_loss / lossv of the variational loss, which a later
+    // hpv_varloss_backward consumes
+    ScopedBuf<float> dfield, dres, del;
+    ScopedBuf<double> dloss;
+    HPV_CK(dfield.alloc(npts)); HPV_CK(dres.alloc(nres)); HPV_CK(del.alloc(c->n_el)); HPV_CK(dloss.alloc(1));
     HPV_CK(cudaMemcpyAsync(dfield.p, hf.data(), npts * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     HpvVarArgs a; fill_var_args(c, a);
     a.n_terms = 1;
     a.terms[0] = hpv_term_zero();
     a.terms[0].ltab = ltab; a.terms[0].rtab = rtab; a.terms[0].s = (float)sc; a.terms[0].px = px; a.terms[0].py = py;
     a.F = nullptr; a.field_in = dfield.p;
+    a.Res = dres.p; a.el_loss = del.p; a.loss = dloss.p;
     const HpvKernelKey k = key_of(c, 0, 0);
     const HpvFwdSmem fs = hpv_fwd_smem(a, hpv_slot_floats(k.dim, k.mx, k.my, k.hp, HPV_THREADS));
     HpvLaunch l; memset(&l, 0, sizeof(l));
@@ -750,9 +810,9 @@ int hpv_project_field(hpv_ctx* c, const double* field, int ltab, int rtab, doubl
     cudaError_t e = hpv_dispatch(k, l);
     c->launches += 1;
     std::vector<float> hr(nres);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(hr.data(), c->Res.p, nres * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    dfield.release();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hr.data(), dres.p, nres * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e2 = cudaStreamSynchronize(c->stream);               // always: the scratch buffers are freed on return
+    if (e == cudaSuccess) e = e2;
     if (e != cudaSuccess) return fail(c, HPV_ERR_CUDA, std::string("hpv_project_field: ") + cudaGetErrorString(e));
     for (size_t i = 0; i < nres; ++i) out[i] = hr[i];
     return HPV_OK;
@@ -787,7 +847,8 @@ static void fill_adam_args(hpv_ctx* c, HpvAdamArgs& a, int update, bool wrote[3]
 
 static void adam_launched(hpv_ctx* c, const bool wrote[3]) {
     c->adam_parity ^= 1;
-    for (int k = 0; k < 3; ++k) if (!wrote[k]) c->mirror_stale[k] = true;
+    c->adam_t += 1.0;
+    for (int k = 0; k < 3; ++k) { c->last_wrote[k] = wrote[k]; if (!wrote[k]) c->mirror_stale[k] = true; }
 }
 
 static int unpad_grad(hpv_ctx* c, int update) {
@@ -834,7 +895,7 @@ int hpv_net_u(hpv_ctx* c, int n, const double* pts, double* u, double* d1, doubl
     const int dim = c->net.dim;
     std::vector<float> hp((size_t)n * dim);
     for (size_t i = 0; i < hp.size(); ++i) hp[i] = (float)pts[i];
-    DevBuf<float> dp, du, dd1, dd2;
+    ScopedBuf<float> dp, du, dd1, dd2;
     HPV_CK(dp.alloc(hp.size()));
     HPV_CK(cudaMemcpyAsync(dp.p, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     if (u) HPV_CK(du.alloc(n));
@@ -855,7 +916,6 @@ int hpv_net_u(hpv_ctx* c, int n, const double* pts, double* u, double* d1, doubl
     if (!r && e == cudaSuccess && d1) e = fetch(dd1, d1, (size_t)n * dim);
     if (!r && e == cudaSuccess && d2) e = fetch(dd2, d2, (size_t)n * dim);
     cudaStreamSynchronize(c->stream);
-    dp.release(); du.release(); dd1.release(); dd2.release();
     if (r) return r;
     if (e != cudaSuccess) return fail(c, HPV_ERR_CUDA, std::string("hpv_net_u: ") + cudaGetErrorString(e));
     return HPV_OK;
@@ -866,6 +926,7 @@ int hpv_set_point_loss(hpv_ctx* c, int slot, int n, const double* pts, const dou
     { int r = need_net(c); if (r) return r; }
     if (slot < 0 || slot >= HPV_MAX_POINT_SETS) return fail(c, HPV_ERR_ARG, "slot out of range");
     PointSet& ps = c->ps[slot];
+    c->epoch++;
     if (n == 0) { ps.active = false; ps.n = 0; return HPV_OK; }
     if (n < 0 || !pts || !target || !a0) return fail(c, HPV_ERR_ARG, "bad point-loss arguments");
     HPV_CK(cudaSetDevice(c->device));
@@ -909,15 +970,18 @@ int hpv_configure_training(hpv_ctx* c, double wv, unsigned mask, int train_eps, 
                            double eps_hat) {
     if (!c) return HPV_ERR_ARG;
     c->wv = wv; c->mask = mask; c->train_eps = train_eps; c->lr = lr; c->b1 = b1; c->b2 = b2; c->eps_hat = eps_hat;
+    c->epoch++;
     return HPV_OK;
 }
 
 // fuse_adam: the step's last gradient reduction also applies the Adam update (single-GPU training step).
-static int loss_and_grad_impl(hpv_ctx* c, bool fuse_adam) {
+#define HPV_HIST_CAP 1024
+static int loss_and_grad_impl(hpv_ctx* c, bool fuse_adam, bool device_hist = false) {
     { int r = need_net(c); if (r) return r; }
     HPV_CK(cudaSetDevice(c->device));
     const bool use_v = c->wv != 0.0;
-    if (use_v || !c->redbuf.p) { int r = ensure_ready(c); if (r) return r; }
+    if (use_v) { int r = ensure_ready(c); if (r) return r; }
+    else { int r = ensure_grad_buffers(c, 0); if (r) return r; }
     // The gradient reduction of a loss must run before the next reverse sweep overwrites the per-CTA partials;
     // the last one of the step also assembles the loss values (saves a launch).
     int acc = 0, pending = -1;
@@ -930,6 +994,10 @@ static int loss_and_grad_impl(hpv_ctx* c, bool fuse_adam) {
     }
     HpvLossArgs la; memset(&la, 0, sizeof(la));
     la.lossv = c->loss.p; la.wv = (float)c->wv; la.use_v = use_v ? 1 : 0; la.out = c->redbuf.p + c->loss_off;
+    if (device_hist) {
+        la.hist = c->hist_ring.p; la.hist_cap = HPV_HIST_CAP; la.hist_t0 = c->hist_t0.p;
+        la.clock = c->adam_clock.p + 3 * c->adam_parity;           // the clock buffer this step's update reads
+    }
     for (int s = 0; s < HPV_MAX_POINT_SETS; ++s) {
         if (!(c->mask & (1u << s)) || !c->ps[s].active) continue;
         PointSet& ps = c->ps[s];
@@ -1021,20 +1089,20 @@ int hpv_peer_connect(hpv_ctx* c, int rank, int nranks, const unsigned char* all_
         c->peer_opened.push_back(q1);
         c->peer_inbox[r] = static_cast<float*>(q0); c->peer_flags[r] = static_cast<unsigned*>(q1);
     }
-    c->peer_rank = rank; c->peer_n = nranks; c->peer_seq = 0;
+    c->peer_rank = rank; c->peer_n = nranks; c->peer_seq = 0; c->epoch++;
     return HPV_OK;
 }
 
 int hpv_adam_step(hpv_ctx* c) {
     { int r = need_net(c); if (r) return r; }
-    if (!c->redbuf.p) return fail(c, HPV_ERR_STATE, "hpv_loss_and_grad has not been called");
+    if (!c->grad_ready) return fail(c, HPV_ERR_STATE, "hpv_loss_and_grad has not been called (for the current network)");
     HPV_CK(cudaSetDevice(c->device));
     return unpad_grad(c, 1);
 }
 
 int hpv_read_losses(hpv_ctx* c, double* out, int n) {
     if (!c || !out || n < 1) return HPV_ERR_ARG;
-    if (!c->redbuf.p) return fail(c, HPV_ERR_STATE, "hpv_loss_and_grad has not been called");
+    if (!c->grad_ready) return fail(c, HPV_ERR_STATE, "hpv_loss_and_grad has not been called (for the current network)");
     HPV_CK(cudaSetDevice(c->device));
     float h[8];
     HPV_CK(cudaMemcpyAsync(h, c->redbuf.p + c->loss_off, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
@@ -1047,7 +1115,7 @@ int hpv_read_losses(hpv_ctx* c, double* out, int n) {
 int hpv_read_losses_and_grad(hpv_ctx* c, double* losses, int nl, double* g, int n, double* ge) {
     { int r = need_net(c); if (r) return r; }
     if (!losses || nl < 1 || !g || n != c->net.n_theta) return fail(c, HPV_ERR_ARG, "bad output buffers");
-    if (!c->redbuf.p) return fail(c, HPV_ERR_STATE, "hpv_loss_and_grad has not been called");
+    if (!c->grad_ready) return fail(c, HPV_ERR_STATE, "hpv_loss_and_grad has not been called (for the current network)");
     HPV_CK(cudaSetDevice(c->device));
     {   // un-pad the gradient and append the loss values: one kernel, one device-to-host copy, one synchronisation
         HpvAdamArgs a;
@@ -1070,7 +1138,7 @@ int hpv_read_losses_and_grad(hpv_ctx* c, double* losses, int nl, double* g, int 
 
 int hpv_read_grad(hpv_ctx* c, double* g, int n, double* ge) {
     { int r = need_net(c); if (r) return r; }
-    if (!c->redbuf.p) return fail(c, HPV_ERR_STATE, "hpv_loss_and_grad has not been called");
+    if (!c->grad_ready) return fail(c, HPV_ERR_STATE, "hpv_loss_and_grad has not been called (for the current network)");
     HPV_CK(cudaSetDevice(c->device));
     return read_grad(c, g, n, ge);
 }
@@ -1085,28 +1153,129 @@ int hpv_reset_optimizer(hpv_ctx* c) {
     HPV_CK(cudaMemcpyAsync(c->adam_clock.p, clock0, sizeof(clock0), cudaMemcpyHostToDevice, c->stream));
     HPV_CK(cudaStreamSynchronize(c->stream));                     // clock0 is on the stack
     c->adam_parity = 0;
+    c->adam_t = 0.0;
     return HPV_OK;
+}
+
+// Capture ONE training step per parity of the optimizer clock (the clock is double-buffered, so the launch arguments
+// have period 2) into executable graphs.  The launches are exactly those of the plain path, including the
+// programmatic dependent launches between them.  Called after at least two plain steps of the current configuration,
+// so that every lazy set-up (launch plans, shared-memory opt-ins, constant-memory mirrors) is behind us and the
+// capture contains kernel (and memset/memcpy) nodes only.
+static int build_step_graphs(hpv_ctx* c, bool want_hist) {
+    for (int i = 0; i < 2; ++i) if (c->step_graph[i]) { cudaGraphExecDestroy(c->step_graph[i]); c->step_graph[i] = nullptr; }
+    HPV_CK(cudaStreamSynchronize(c->stream));
+    const int parity0 = c->adam_parity;
+    const double t_before = c->adam_t;
+    const bool stale_before[3] = {c->mirror_stale[0], c->mirror_stale[1], c->mirror_stale[2]};
+    int rc = HPV_OK;
+    for (int i = 0; i < 2 && rc == HPV_OK; ++i) {
+        const int par = parity0 ^ i;
+        const long long l0 = c->launches;
+        c->adam_parity = par;
+        c->used_kinds = 0;
+        cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) { rc = fail(c, HPV_ERR_CUDA, std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e)); break; }
+        c->capturing = true;
+        int r = loss_and_grad_impl(c, true, want_hist);
+        c->capturing = false;
+        cudaGraph_t g = nullptr;
+        e = cudaStreamEndCapture(c->stream, &g);
+        c->graph_launches = (int)(c->launches - l0);
+        c->launches = l0;
+        c->graph_kinds = c->used_kinds;
+        for (int k = 0; k < 3; ++k) c->graph_wrote[k] = c->last_wrote[k];
+        if (r) { if (g) cudaGraphDestroy(g); rc = r; break; }
+        if (e != cudaSuccess) { rc = fail(c, HPV_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e)); break; }
+        e = cudaGraphInstantiate(&c->step_graph[par], g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { c->step_graph[par] = nullptr; rc = fail(c, HPV_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+    }
+    // the captured launches did not run: restore the host-side bookkeeping they advanced
+    c->adam_parity = parity0; c->adam_t = t_before;
+    for (int k = 0; k < 3; ++k) c->mirror_stale[k] = stale_before[k];
+    if (rc != HPV_OK) {
+        for (int i = 0; i < 2; ++i) if (c->step_graph[i]) { cudaGraphExecDestroy(c->step_graph[i]); c->step_graph[i] = nullptr; }
+        return rc;
+    }
+    c->graph_epoch = c->epoch; c->graph_hist = want_hist;
+    return HPV_OK;
+}
+
+static bool graphs_valid(const hpv_ctx* c, bool want_hist) {
+    return c->step_graph[0] && c->step_graph[1] && c->graph_epoch == c->epoch && (!want_hist || c->graph_hist);
 }
 
 int hpv_train_steps(hpv_ctx* c, int nsteps, double* hist) {
     { int r = need_net(c); if (r) return r; }
     if (nsteps < 0) return fail(c, HPV_ERR_ARG, "nsteps < 0");
-    DevBuf<float> dh;
-    if (hist && nsteps) HPV_CK(dh.alloc((size_t)nsteps * 6));
-    for (int it = 0; it < nsteps; ++it) {
-        // one launch sequence per step: forward, adjoint projection, reverse sweep, reduction + losses + Adam
-        int r = loss_and_grad_impl(c, true);
-        if (!r && hist)       // the loss values are those of the parameters the gradient was taken at
-            HPV_CK(cudaMemcpyAsync(dh.p + (size_t)it * 6, c->redbuf.p + c->loss_off, 6 * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
-        if (r) { dh.release(); return r; }
+    HPV_CK(cudaSetDevice(c->device));
+    const bool want_hist = hist && nsteps;
+    // Graph replay for single-GPU steps (the peer exchange takes a per-step sequence number from the host).
+    const bool graph = c->use_graph && c->peer_n <= 1;
+    if (!graph) {
+        ScopedBuf<float> dh;
+        if (want_hist) HPV_CK(dh.alloc((size_t)nsteps * 6));
+        for (int it = 0; it < nsteps; ++it) {
+            // one launch sequence per step: forward, adjoint projection, reverse sweep, reduction + losses + Adam
+            int r = loss_and_grad_impl(c, true);
+            if (!r && want_hist)       // the loss values are those of the parameters the gradient was taken at
+                HPV_CK(cudaMemcpyAsync(dh.p + (size_t)it * 6, c->redbuf.p + c->loss_off, 6 * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+            if (r) { cudaStreamSynchronize(c->stream); return r; }
+        }
+        if (want_hist) {
+            std::vector<float> h((size_t)nsteps * 6);
+            HPV_CK(cudaMemcpyAsync(h.data(), dh.p, h.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+            HPV_CK(cudaStreamSynchronize(c->stream));
+            for (size_t i = 0; i < h.size(); ++i) hist[i] = h[i];
+        }
+        return HPV_OK;
     }
-    if (hist && nsteps) {
-        std::vector<float> h((size_t)nsteps * 6);
-        HPV_CK(cudaMemcpyAsync(h.data(), dh.p, h.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-        HPV_CK(cudaStreamSynchronize(c->stream));
-        for (size_t i = 0; i < h.size(); ++i) hist[i] = h[i];
+    if (want_hist && !c->hist_ring.p) { HPV_CK(c->hist_ring.alloc((size_t)HPV_HIST_CAP * 8)); HPV_CK(c->hist_t0.alloc(1)); }
+    if (c->plain_epoch != c->epoch) { c->plain_epoch = c->epoch; c->plain_steps = 0; }
+    int done = 0;
+    std::vector<float> hh;
+    while (done < nsteps) {
+        int chunk = nsteps - done;
+        if (want_hist && chunk > HPV_HIST_CAP) chunk = HPV_HIST_CAP;
+        if (want_hist) {
+            const double t0 = c->adam_t;                        // step counter at the first step of this chunk
+            HPV_CK(cudaMemcpyAsync(c->hist_t0.p, &t0, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            HPV_CK(cudaStreamSynchronize(c->stream));           // t0 is on the stack
+        }
+        for (int it = 0; it < chunk; ++it) {
+            if (!graphs_valid(c, want_hist) && c->plain_steps >= 2 && chunk - it >= 1) {
+                int r = build_step_graphs(c, want_hist || c->graph_hist);
+                if (r) return r;
+            }
+            if (graphs_valid(c, want_hist)) {
+                {
+                    // the constant-memory copies the step's kernels read must be this context's and current (another
+                    // context of the device may have taken them over since the last replay); inside the replays the
+                    // optimizer keeps them current
+                    for (int k = 0; k < 3; ++k)
+                        if ((c->graph_kinds & (1u << k)) || c->mirror[k]) { int r = refresh_mirror(c, k); if (r) return r; }
+                }
+                HPV_CK(cudaGraphLaunch(c->step_graph[c->adam_parity], c->stream));
+                c->launches += c->graph_launches;
+                c->adam_parity ^= 1;
+                c->adam_t += 1.0;
+                for (int k = 0; k < 3; ++k) if (!c->graph_wrote[k]) c->mirror_stale[k] = true;
+            } else {
+                int r = loss_and_grad_impl(c, true, want_hist);
+                if (r) return r;
+                c->plain_steps += 1;
+            }
+        }
+        if (want_hist) {
+            hh.resize((size_t)chunk * 8);
+            HPV_CK(cudaMemcpyAsync(hh.data(), c->hist_ring.p, hh.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+            HPV_CK(cudaStreamSynchronize(c->stream));
+            for (int i = 0; i < chunk; ++i)
+                for (int j = 0; j < 6; ++j) hist[(size_t)(done + i) * 6 + j] = hh[(size_t)i * 8 + j];
+        }
+        done += chunk;
     }
-    dh.release();
     return HPV_OK;
 }
 
@@ -1116,10 +1285,10 @@ int hpv_kernel_info(hpv_ctx* c, int* info, int n) {
     if (!c || !info) return HPV_ERR_ARG;
     HPV_CK(cudaSetDevice(c->device));
     { int r = ensure_ready(c); if (r) return r; }
-    const int v[13] = {c->n_sm, c->part.n_ctas, HPV_THREADS, (int)c->fwd_smem, c->fwd_ctas_per_sm,
+    const int v[14] = {c->n_sm, c->part.n_ctas, HPV_THREADS, (int)c->fwd_smem, c->fwd_ctas_per_sm,
                        c->bwd_grid, c->bwd_block, (int)c->bwd_smem, c->bwd_ctas_per_sm,
-                       c->adj_grid, (int)c->adj_smem, c->net.hp, bwd_key_of(c).dir};
-    for (int i = 0; i < n && i < 13; ++i) info[i] = v[i];
+                       c->adj_grid, (int)c->adj_smem, c->net.hp, bwd_key_of(c).dir, c->fwd_tc_active ? 1 : 0};
+    for (int i = 0; i < n && i < 14; ++i) info[i] = v[i];
     return HPV_OK;
 }
 
@@ -1127,7 +1296,7 @@ int hpv_probe_fp32_peak(hpv_ctx* c, int variant, double* tflops) {
     if (!c || !tflops) return HPV_ERR_ARG;
     HPV_CK(cudaSetDevice(c->device));
     const int grid = c->n_sm * 8, block = 256, iters = 4096;
-    DevBuf<float> out;
+    ScopedBuf<float> out;
     HPV_CK(out.alloc((size_t)grid * block));
     cudaEvent_t e0, e1;
     HPV_CK(cudaEventCreate(&e0)); HPV_CK(cudaEventCreate(&e1));
@@ -1140,7 +1309,6 @@ int hpv_probe_fp32_peak(hpv_ctx* c, int variant, double* tflops) {
     float ms = 0.0f;
     HPV_CK(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    out.release();
     const double flops = (double)grid * block * iters * 64.0 * 2.0 * reps;
     *tflops = flops / (ms * 1e-3) / 1e12;
     return HPV_OK;

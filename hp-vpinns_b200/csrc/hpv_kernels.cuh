@@ -14,6 +14,18 @@ __global__ void __launch_bounds__(HPV_THREADS, (HpvMode<DIM, MX, MY>::NCH >= 4 ?
     hpv_varfwd_body<DIM, MX, MY, HP, ACT>(c, a);
 }
 
+// Tensor-core form of the forward kernel (hpv_varfwd_tc.cuh): two CTAs per SM when a CTA's accumulators and A operands
+// fit 256 TMEM columns, one otherwise.
+template <int DIM, int MX, int MY, int HP, int ACT>
+__global__ void __launch_bounds__(HPV_THREADS, (hpv_tc_tmem_need(HpvMode<DIM, MX, MY>::NCH, HP) <= 256 ? 2 : 1))
+hpv_varfwd_tc_kernel(const __grid_constant__ HpvVarArgs a) {
+    extern __shared__ __align__(128) unsigned char hpv_smem_tc[];
+    HpvCta c;
+    c.tid = threadIdx.x; c.nthreads = blockDim.x; c.bid = blockIdx.x; c.nblocks = gridDim.x;
+    c.smem = hpv_smem_tc; c.emu = nullptr;
+    if constexpr (hpv_tc_supported(HpvMode<DIM, MX, MY>::NCH, HP)) hpv_varfwd_tc_body<DIM, MX, MY, HP, ACT>(c, a);
+}
+
 // Launch bounds of the reverse sweep.  The host picks the number of warps per SM and their grouping into CTAs per
 // launch (plan_bwd): the warps share nothing but the constant parameters, so a CTA is only a resource container.
 // The kernel is bound by shared-memory / constant-load latency, so resident warps matter more than registers:
@@ -81,6 +93,21 @@ static cudaError_t hpv_do(const HpvLaunch& l) {
         }
         if (l.op == 3) { void* p = nullptr; err = cudaGetSymbolAddress(&p, hpv_c_theta); *l.out = (long long)(uintptr_t)p; return err; }
         k<<<l.grid, l.block, l.smem, l.stream>>>(*l.var);
+    } else if constexpr (KIND == HPV_K_VARFWD_TC) {
+        if constexpr (!hpv_tc_supported(HpvMode<DIM, MX, MY>::NCH, HP)) {
+            return cudaErrorInvalidValue;
+        } else {
+            auto k = hpv_varfwd_tc_kernel<DIM, MX, MY, HP, ACT>;
+            if ((err = hpv_prepare(k, l.smem, prepared)) != cudaSuccess) return err;
+            if (l.op == 1) {
+                int n = 0;
+                err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, l.block, l.smem);
+                const int by_tmem = 512 / hpv_tc_tmem_cols(HpvMode<DIM, MX, MY>::NCH, HP);
+                *l.out = n < by_tmem ? n : by_tmem;
+                return err;
+            }
+            k<<<l.grid, l.block, l.smem, l.stream>>>(*l.var);
+        }
     } else if constexpr (KIND == HPV_K_MLPBWD) {
         auto k = hpv_mlpbwd_kernel<DIM, MX, MY, HP, ACT>;
         if (l.op == 2) {

@@ -135,7 +135,10 @@ __global__ void __launch_bounds__(1024) hpv_gradreduce_kernel(const HpvGradReduc
             g = hpv_peer_exchange(pa, blockIdx.x, threadIdx.x, i < a.n ? g : 0.0f);
             if (i < a.n) a.grad_pad[i] = g;
         }
-        if (has_adam) {
+        // a timed-out exchange (a peer died) leaves stale inbox data in g: keep the parameters as they are; the host
+        // reads the error word after its next synchronisation (check_peer_error) and fails the call
+        const bool exchange_failed = has_peer && *reinterpret_cast<volatile unsigned*>(pa.err) != 0u;
+        if (has_adam && !exchange_failed) {
             const double lr_t = hpv_adam_clock(ad, i == 0);
             if (i < a.n) {
                 const int r = ad.ref_index[i];
@@ -154,8 +157,12 @@ cudaError_t hpv_launch_gradreduce(const HpvGradReduceArgs& a, const HpvLossArgs*
     memset(&a0, 0, sizeof(a0));
     HpvPeerArgs p0;
     memset(&p0, 0, sizeof(p0));
-    // 32 groups of partials per CTA when there are many of them (the sum is latency-bound otherwise)
-    const int block = a.n_parts >= 128 ? 1024 : 256;
+    // 32 groups of partials per CTA when there are many of them (the sum is latency-bound otherwise).  With the peer
+    // exchange every CTA spins on flags that the matching CTA of the other ranks sets: all CTAs of the grid must be
+    // co-resident (forward progress must not depend on the dispatch order), which 1024-thread CTAs (2 per SM)
+    // only guarantee up to 2 x 148 of them -- beyond that the grid runs 256-thread CTAs (8 per SM).
+    int block = a.n_parts >= 128 ? 1024 : 256;
+    if (peer && nred + 1 > 256) block = 256;
     return hpv_launch_pdl(hpv_gradreduce_kernel, nred + (la ? 1 : 0), block, 0, s, a, la ? *la : l0, nred, adam ? *adam : a0,
                           adam ? 1 : 0, peer ? *peer : p0, peer ? 1 : 0, loss_off / 32);
 }

@@ -5,6 +5,7 @@
 #include <string.h>
 #include "hpv_varbwd.cuh"
 #include "hpv_points.cuh"
+#include "hpv_varfwd_tc.cuh"
 
 // dir != 0 (reverse sweep only): the directional mode HpvMode<2, 1, 0> instead of <2, 1, 1>.
 // Launch with programmatic stream serialisation: the kernel's CTAs may start before the previous kernel of the
@@ -31,7 +32,7 @@ inline cudaError_t hpv_launch_pdl(void (*kernel)(KArgs...), int grid, int block,
 
 struct HpvKernelKey { int dim, mx, my, hp, act, dir; };
 
-enum { HPV_K_VARFWD = 0, HPV_K_MLPBWD = 1, HPV_K_POINTS = 2 };
+enum { HPV_K_VARFWD = 0, HPV_K_MLPBWD = 1, HPV_K_POINTS = 2, HPV_K_VARFWD_TC = 3 };
 
 // op: 0 = launch, 1 = query resident CTAs per SM for (block, smem) into *out, 4 = (reverse sweep) the largest
 // block size the kernel was compiled for, 2 = shared memory bytes of the
@@ -52,7 +53,8 @@ struct HpvLaunch {
 #define HPV_DECL(hp) \
     cudaError_t hpv_dispatch_h##hp##_fwd(const HpvKernelKey& k, const HpvLaunch& l); \
     cudaError_t hpv_dispatch_h##hp##_bwd(const HpvKernelKey& k, const HpvLaunch& l); \
-    cudaError_t hpv_dispatch_h##hp##_pts(const HpvKernelKey& k, const HpvLaunch& l);
+    cudaError_t hpv_dispatch_h##hp##_pts(const HpvKernelKey& k, const HpvLaunch& l); \
+    cudaError_t hpv_dispatch_h##hp##_fwdtc(const HpvKernelKey& k, const HpvLaunch& l);
 HPV_DECL(8)
 HPV_DECL(20)
 HPV_DECL(32)
@@ -63,6 +65,7 @@ inline cudaError_t hpv_dispatch(const HpvKernelKey& k, const HpvLaunch& l) {
     if (k.hp == hpv) { \
         if (l.kind == HPV_K_VARFWD) return hpv_dispatch_h##hpv##_fwd(k, l); \
         if (l.kind == HPV_K_MLPBWD) return hpv_dispatch_h##hpv##_bwd(k, l); \
+        if (l.kind == HPV_K_VARFWD_TC) return hpv_dispatch_h##hpv##_fwdtc(k, l); \
         return hpv_dispatch_h##hpv##_pts(k, l); \
     }
     HPV_CASE(8)
@@ -81,6 +84,9 @@ struct HpvLossArgs {
     const double* lossv; float wv; int use_v;
     const float* blk[HPV_MAX_POINT_SETS]; int nblk[HPV_MAX_POINT_SETS];
     float* out;     // [8]: total, lossv, point losses
+    // optional device-side loss history (graph-replayed training steps cannot take a per-step destination from the
+    // host): the values also go to hist[8 * (t - t0)] with t the optimizer's step counter (clock[2]) -- 0 <= t - t0 < hist_cap
+    float* hist; const double* clock; const double* hist_t0; int hist_cap;
 };
 #if defined(__CUDACC__)
 __device__ inline void hpv_losses_warp(const HpvLossArgs& a, int lane) {
@@ -97,6 +103,14 @@ __device__ inline void hpv_losses_warp(const HpvLossArgs& a, int lane) {
     if (lane == 0) {
         a.out[0] = total; a.out[1] = lv;
         for (int s = 0; s < HPV_MAX_POINT_SETS; ++s) a.out[2 + s] = pl[s];
+        if (a.hist) {
+            const long long idx = (long long)(a.clock[2] - a.hist_t0[0]);
+            if (idx >= 0 && idx < (long long)a.hist_cap) {
+                float* h = a.hist + idx * 8;
+                h[0] = total; h[1] = lv;
+                for (int s = 0; s < HPV_MAX_POINT_SETS; ++s) h[2 + s] = pl[s];
+            }
+        }
     }
 }
 #endif

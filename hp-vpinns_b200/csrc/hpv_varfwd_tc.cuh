@@ -1,0 +1,527 @@
+// Forward kernel of the variational loss, tensor-core form (sm_100a): the same path as hpv_varfwd.cuh --
+// net_u and input derivatives at the tensor Gauss-Lobatto points (P2D:81-83,158-185), projection on the test
+// functions by sum factorisation (P2D:94-115), Res = U - F_ext, element loss, lossv (P2D:118-120) -- with
+//   * the hidden-layer products of the MLP on the 5th-generation tensor cores: tcgen05.mma kind::tf32, M = 128
+//     quadrature points, N = 32 (output units, padded), K = 8 per instruction; the activations of a layer are the A
+//     operand and live in tensor memory (TMEM), written there by the threads that computed them (tcgen05.st); the
+//     weights with the bias as an extra input row are K-major B tiles in shared memory; the pre-activations of the
+//     next layer accumulate in TMEM and come back with tcgen05.ld.  fp32-class accuracy from TF32 products by the
+//     3-term split  A.B ~ Ahi.Bhi + Alo.Bhi + Ahi.Blo  (hi = the TF32 part of the fp32 value, lo = the rest);
+//   * the test-function tables staged ONCE per CTA by the bulk-copy engine (TMA, cp.async.bulk + mbarrier) into a
+//     region of their own -- the activations no longer need shared memory, so nothing aliases the tables.
+// Thread layout of the MLP phase: CTA = 256 threads = 8 warps; warp w works on TMEM sub-partition w % 4 (32 of the
+// tile's 128 points, one per lane) and on the units [HP/2 (w / 4), HP/2 (w / 4) + HP/2) of every layer; layer 1 and
+// the output layer (K = 2 and N = 1) stay on the FMA pipe.  One elected thread issues the MMAs of a layer, channel
+// by channel, each channel committing to its own mbarrier so that the value channel's tanh overlaps the tangent
+// channels' products; two CTAs per SM (256 TMEM columns each) overlap one CTA's products with the other's
+// activations.  The projection phases are those of hpv_varfwd.cuh.
+#pragma once
+#include "hpv_cta.cuh"
+#include "hpv_slot.cuh"
+#include "hpv_umma.cuh"
+#include "hpv_varfwd.cuh"
+
+#define HPV_TC_NPAD 32                         // N of the MMA instruction (output units padded)
+#define HPV_TC_MTILE 128                       // M: quadrature points per MMA tile
+
+template <int HP> struct HpvTcDims {
+    static constexpr int KP = ((HP + 1 + 7) / 8) * 8;          // inputs + bias row, padded to the instruction's K = 8
+    static constexpr int HPH = HP / 2;                         // units per thread
+};
+// TMEM columns of a CTA: NCH accumulators of NPAD columns, then the A operands (hi, then lo; KP columns per channel).
+HPV_HD constexpr int hpv_tc_tmem_need(int nch, int hp) { return nch * HPV_TC_NPAD + 2 * nch * (((hp + 1 + 7) / 8) * 8); }
+HPV_HD constexpr int hpv_tc_tmem_cols(int nch, int hp) { return hpv_tc_tmem_need(nch, hp) <= 256 ? 256 : 512; }
+HPV_HD constexpr bool hpv_tc_supported(int nch, int hp) { return hpv_tc_tmem_need(nch, hp) <= 512; }
+
+struct HpvFwdTcSmem {
+    int xi1, G, red, flag, tab[HPV_NTAB], P, th, part, B, bar, total;   // offsets in floats
+    int GS, RMAX, th_n, B_layer;
+};
+
+HPV_HD HpvFwdTcSmem hpv_fwd_tc_smem(const HpvVarArgs& a, int dim, int hp, int nch) {
+    HpvFwdTcSmem s;
+    const int kp = ((hp + 1 + 7) / 8) * 8;
+    int o = 0;
+    s.xi1 = o; o += hpv_align4(a.Q);
+    s.GS = hpv_align4(HPV_CT * HPV_THREADS + 2 * a.Q);
+    int rmax = (HPV_CT * HPV_THREADS) / a.Q + 2;
+    s.RMAX = rmax < a.rows ? rmax : a.rows;
+    s.G = o; o += a.n_terms * s.GS;
+    s.red = o; o += 2 * HPV_THREADS;
+    s.flag = o; o += 4;
+    const int m = hpv_tab_mask(a);
+    for (int t = 0; t < HPV_NTAB; ++t) {
+        s.tab[t] = -1;
+        if (m & (1 << t)) { s.tab[t] = o; o += a.Q * HPV_NP; }
+    }
+    s.P = o; o += a.n_terms * s.RMAX * HPV_NP;
+    s.th_n = hpv_align4((dim + 1) * hp + hp + 4);             // W1, b1, Wo, bo
+    s.th = o; o += s.th_n;
+    s.part = o; o += nch * HPV_TC_MTILE;
+    o = (o + 31) & ~31;                                       // B tiles: 128-byte aligned
+    s.B_layer = 2 * kp * HPV_TC_NPAD;                         // hi tile, lo tile
+    s.B = o; o += (a.nhid - 1 > 0 ? a.nhid - 1 : 0) * s.B_layer;
+    s.bar = o; o += 2 * (HPV_NFIELDS + 1) + 2;                // mbarriers (8 bytes each): one per channel + tables; TMEM base
+    s.total = o;
+    return s;
+}
+
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ bool hpv_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// N consecutive TMEM columns of this thread's lane <-> registers (N = HP/2: 4, 10 or 16).
+template <int N>
+__device__ __forceinline__ void hpv_tmem_ld_n(uint32_t taddr, float* v) {
+    static_assert(N % 2 == 0 && N <= 16, "unsupported column count");
+    int c = 0;
+#pragma unroll
+    for (; c + 8 <= N; c += 8) {
+        uint32_t r[8];
+        hpv_tmem_ld8(taddr + c, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[c + j] = __uint_as_float(r[j]);
+    }
+    if (N - c >= 4) {
+        uint32_t r[4];
+        hpv_tmem_ld4(taddr + c, r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[c + j] = __uint_as_float(r[j]);
+        c += 4;
+    }
+    if (N - c >= 2) {
+        uint32_t r[2];
+        hpv_tmem_ld2(taddr + c, r);
+        v[c] = __uint_as_float(r[0]); v[c + 1] = __uint_as_float(r[1]);
+    }
+}
+template <int N>
+__device__ __forceinline__ void hpv_tmem_st_n(uint32_t taddr, const uint32_t* v) {
+    int c = 0;
+#pragma unroll
+    for (; c + 8 <= N; c += 8) {
+        uint32_t r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = v[c + j];
+        hpv_tmem_st8(taddr + c, r);
+    }
+    if (N - c >= 4) { hpv_tmem_st4(taddr + c, v[c], v[c + 1], v[c + 2], v[c + 3]); c += 4; }
+    if (N - c >= 2) hpv_tmem_st2(taddr + c, v[c], v[c + 1]);
+}
+
+// hi = the TF32 part of x (low 13 mantissa bits cleared), lo = x - hi (exact).  Truncation instead of rounding
+// keeps the split at one LOP3 + one FADD; lo then carries up to 13 significant bits of which the tensor core uses
+// 11: 2^-21 |x|, the same order as the dropped lo.lo term.
+__device__ __forceinline__ void hpv_split_trunc(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+// The MMAs of one hidden-layer product for all channels, issued by one thread.  TB (TMEM base of this CTA), the
+// column offsets and the descriptor strides are compile-time constants and the shared-memory addresses are uniform,
+// so every operand sits in a uniform register without a transfer from the vector registers: the instructions go out
+// back to back (tools/probes/umma_probe.cu, tests 10 and 13: 17-20 cycles per instruction against 90-190 with
+// operands that have to be moved per instruction).
+template <uint32_t TB, int NCH, int KP>
+__device__ __forceinline__ void hpv_tc_issue_layer(uint32_t bhi, uint32_t blo, uint64_t* bar) {
+    constexpr uint32_t colD = 0, colAhi = NCH * HPV_TC_NPAD, colAlo = colAhi + NCH * KP;
+    constexpr uint32_t idesc = hpv_umma_idesc_tf32(HPV_TC_MTILE, HPV_TC_NPAD, 0, 0);
+    constexpr uint32_t LBO = HPV_TC_NPAD * 16, SBO = 128;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {                       // (Alo, Bhi), (Ahi, Blo), (Ahi, Bhi): small terms first
+#pragma unroll
+            for (int ks = 0; ks < KP / 8; ++ks) {
+                const uint64_t bd = hpv_umma_desc((term == 1 ? blo : bhi) + ks * 2 * LBO, LBO, SBO);
+                hpv_umma_ts(TB + colD + c * HPV_TC_NPAD, TB + (term == 0 ? colAlo : colAhi) + c * KP + ks * 8, bd, idesc, (term | ks) != 0);
+            }
+        }
+        hpv_umma_commit(&bar[c]);
+    }
+}
+
+template <int DIM, int MX, int MY, int HP, int ACT>
+__device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVarArgs& a) {
+    typedef HpvMode<DIM, MX, MY> M;
+    constexpr int NCH = M::NCH, KP = HpvTcDims<HP>::KP, HPH = HpvTcDims<HP>::HPH, NPR = HPH / 2;
+    constexpr uint32_t TCOLS = (NCH * HPV_TC_NPAD + 2 * NCH * KP) <= 256 ? 256u : 512u;
+    static_assert(HPH % 2 == 0, "HP/2 must be even (packed pairs)");
+    const int T = c.nthreads, tid = c.tid;
+    const HpvFwdTcSmem L = hpv_fwd_tc_smem(a, DIM, HP, NCH);
+    float* sm = reinterpret_cast<float*>(c.smem);
+    float* s_xi1 = sm + L.xi1;
+    float* s_G = sm + L.G;
+    float* s_P = sm + L.P;
+    float* s_red = sm + L.red;
+    float* s_th = sm + L.th;
+    float* s_part = sm + L.part;
+    uint32_t* s_B = reinterpret_cast<uint32_t*>(sm + L.B);
+    int* s_flag = reinterpret_cast<int*>(sm + L.flag);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(sm + L.bar);           // [0..NCH): channels, [HPV_NFIELDS]: tables
+    uint32_t* s_tbase = reinterpret_cast<uint32_t*>(s_bar + HPV_NFIELDS + 1);
+    const int Q = a.Q, nhid = a.nhid;
+    const int warp = tid >> 5, lane = tid & 31, sub = warp & 3, half = warp >> 2, u0 = half * HPH;
+    const int prow = sub * 32 + lane;
+
+    // ---- one-time set-up: TMEM, mbarriers, tables by TMA, parameters, weight tiles ----
+    if (warp == 0) hpv_tmem_alloc(s_tbase, TCOLS);
+    if (tid == 0) {
+        for (int i = 0; i <= HPV_NFIELDS; ++i) hpv_mbar_init(&s_bar[i], 1);
+        hpv_mbar_init_fence();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // the test-function tables: one bulk copy each (the copy engine works while the CTA builds the weight tiles)
+        uint32_t bytes = 0;
+        for (int t = 0; t < HPV_NTAB; ++t) if (L.tab[t] >= 0) bytes += (uint32_t)(Q * HPV_NP * 4);
+        hpv_mbar_expect_tx(&s_bar[HPV_NFIELDS], bytes);
+        for (int t = 0; t < HPV_NTAB; ++t)
+            if (L.tab[t] >= 0) hpv_bulk_g2s(sm + L.tab[t], a.tab[t], (uint32_t)(Q * HPV_NP * 4), &s_bar[HPV_NFIELDS]);
+    }
+    for (int i = tid; i < Q; i += T) s_xi1[i] = a.xi1[i];
+    {
+        // W1 [DIM][HP], b1 [HP] | Wo [HP], bo
+        const float* tg = a.theta_pad;
+        const int n1 = (DIM + 1) * HP;
+        for (int i = tid; i < n1; i += T) s_th[i] = tg[i];
+        for (int i = tid; i < HP + 4; i += T) s_th[n1 + i] = tg[a.off_wo + i];
+        // B tiles of the hidden layers l = 1 .. nhid-1:  B[n][k] = W_l[k][n] (k < HP), b_l[n] (k = HP), 0 otherwise
+        const int per_layer = KP * HPV_TC_NPAD;
+        for (int i = tid; i < (nhid - 1) * per_layer; i += T) {
+            const int l = i / per_layer, r = i - l * per_layer, n = r / KP, k = r - n * KP;
+            const float* W = tg + hpv_off_wl(DIM, HP, l + 1);
+            float v = 0.0f;
+            if (n < HP) v = k < HP ? W[k * HP + n] : (k == HP ? W[HP * HP + n] : 0.0f);
+            uint32_t hi, lo;
+            hpv_split_trunc(v, hi, lo);
+            const int w = (k >> 2) * (HPV_TC_NPAD * 4) + n * 4 + (k & 3);
+            s_B[l * L.B_layer + w] = hi;
+            s_B[l * L.B_layer + per_layer + w] = lo;
+        }
+    }
+    const float eps = a.eps[0];
+    float coef[HPV_MAX_TERMS][HPV_NFIELDS];
+#pragma unroll
+    for (int t = 0; t < HPV_MAX_TERMS; ++t)
+#pragma unroll
+        for (int f = 0; f < HPV_NFIELDS; ++f)
+            coef[t][f] = (t < a.n_terms) ? fmaf(eps, a.terms[t].a1[f], a.terms[t].a0[f]) : 0.0f;
+    hpv_fence_proxy_async();                   // the weight tiles were written with ordinary stores; the tensor core reads them
+    hpv_tc_fence_before();
+    __syncthreads();
+    hpv_tc_fence_after();
+    const uint32_t tb = *s_tbase;
+    if (TCOLS == 256u ? (tb != 0u && tb != 256u) : (tb != 0u)) { asm volatile("trap;"); }     // the issue code is specialised on the base
+    const uint32_t lane_base = (uint32_t)(sub * 32) << 16;
+    constexpr uint32_t colD = 0, colAhi = NCH * HPV_TC_NPAD, colAlo = colAhi + NCH * KP;
+    // constant columns of the A operands: input HP of the value channel is the bias input 1, the rest of the padding 0
+    if (half == 0) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+#pragma unroll
+            for (int k = HP; k < KP; k += 2) {
+                hpv_tmem_st2(tb + lane_base + colAhi + ch * KP + k, (ch == 0 && k == HP) ? __float_as_uint(1.0f) : 0u, 0u);
+                hpv_tmem_st2(tb + lane_base + colAlo + ch * KP + k, 0u, 0u);
+            }
+        }
+        hpv_tmem_wait_st();
+    }
+    hpv_mbar_wait(&s_bar[HPV_NFIELDS], 0);      // tables have landed
+
+    const int kt = tid >> 4, rt = tid & 15;
+    float U[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) U[i][j] = 0.0f;
+
+    const int tpe = a.tiles_per_el;
+    const int npts_el = a.rows * Q;
+    int t_cur = a.cta_tile_begin[c.bid];
+    const int t_end = a.cta_tile_begin[c.bid + 1];
+    uint32_t phase = 0;
+    const float* W1 = s_th;
+    const float* b1 = s_th + DIM * HP;
+    const float* Wo = s_th + (DIM + 1) * HP;
+
+    constexpr int CHUNK_TILES = HPV_CT * HPV_THREADS / HPV_FWD_TILE;
+    while (t_cur < t_end) {
+        const int e = t_cur / tpe, k0 = t_cur - e * tpe;
+        int nt = tpe - k0;
+        if (nt > CHUNK_TILES) nt = CHUNK_TILES;
+        if (nt > t_end - t_cur) nt = t_end - t_cur;
+        const int p0 = k0 * HPV_FWD_TILE;
+        int p1 = (k0 + nt) * HPV_FWD_TILE;
+        if (p1 > npts_el) p1 = npts_el;
+        const int nmt = (p1 - p0 + HPV_TC_MTILE - 1) / HPV_TC_MTILE;            // MMA tiles of 128 points in this chunk
+        const int ja = p0 / Q, jb = (p1 - 1) / Q, nrows = jb - ja + 1, base = ja * Q;
+        const float lox = a.el_geom[4 * e + 0], hwx = a.el_geom[4 * e + 1];
+        const float loy = a.el_geom[4 * e + 2], hwy = a.el_geom[4 * e + 3];
+
+        // (1) clear the field rows of this chunk
+        for (int t = 0; t < a.n_terms; ++t)
+            for (int i = tid; i < nrows * Q; i += T) s_G[t * L.GS + i] = 0.0f;
+        // (no barrier needed here: the first barrier of the MLP phase below orders the clears before the field stores)
+
+        // (2) network and input derivatives at the quadrature points, 128 points at a time
+#pragma unroll 1
+        for (int mt = 0; mt < nmt; ++mt) {
+            const int p = p0 + mt * HPV_TC_MTILE + prow;
+            const bool valid = p < p1;
+            const int pc = valid ? p : p0;
+            const int j = pc / Q, i = pc - j * Q;
+            const float x = fmaf(hwx, s_xi1[i], lox);
+            const float y = (DIM == 2) ? fmaf(hwy, s_xi1[j], loy) : 0.0f;
+            HpvState<DIM, MX, MY, HPH> s;
+            // first layer, this thread's units: z = b1 + x W1[0,:] (+ y W1[1,:]); dz/dx = W1[0,:]; d2z = 0
+            {
+                const hpv_pair xx = hpv_dup(x), yy = hpv_dup(y);
+#pragma unroll
+                for (int m = 0; m < NPR; ++m) {
+                    const int u = u0 + 2 * m;
+                    const hpv_pair wx = hpv_pack(W1[u], W1[u + 1]);
+                    hpv_pair zz = hpv_fma2r(xx, wx, hpv_pack(b1[u], b1[u + 1]));
+                    if constexpr (DIM == 2) {
+                        const hpv_pair wy = hpv_pack(W1[HP + u], W1[HP + u + 1]);
+                        zz = hpv_fma2r(yy, wy, zz);
+                        if constexpr (M::DY) s.dy.p[m] = wy;
+                    }
+                    s.v.p[m] = zz;
+                    if constexpr (M::DX) s.dx.p[m] = wx;
+                    if constexpr (M::EX) s.ex.p[m] = hpv_dup(0.0f);
+                    if constexpr (M::EY) s.ey.p[m] = hpv_dup(0.0f);
+                }
+            }
+#pragma unroll 1
+            for (int l = 1; l <= nhid; ++l) {
+                if (l > 1) {
+                    // pre-activations of hidden layer l from TMEM, channel by channel as the products complete
+                    hpv_each_ch<M>(s, [&](hpv_pair* zp, int ch) {
+                        hpv_mbar_wait(&s_bar[ch], phase);
+                        hpv_tc_fence_after();
+                        float v[HPH];
+                        hpv_tmem_ld_n<HPH>(tb + lane_base + colD + ch * HPV_TC_NPAD + u0, v);
+                        hpv_tmem_wait_ld();
+#pragma unroll
+                        for (int m = 0; m < NPR; ++m) zp[m] = hpv_pack(v[2 * m], v[2 * m + 1]);
+                    });
+                    phase ^= 1;
+                }
+                hpv_activate<DIM, MX, MY, HPH, ACT>(s);                  // post-activations h, dh, d2h of layer l
+                if (l == nhid) break;
+                // split and store as the A operand of the next product
+                hpv_each_ch<M>(s, [&](hpv_pair* hp_, int ch) {
+                    uint32_t hi[HPH], lo[HPH];
+#pragma unroll
+                    for (int m = 0; m < NPR; ++m) {
+                        float h0, h1;
+                        hpv_unpack(hp_[m], h0, h1);
+                        hpv_split_trunc(h0, hi[2 * m], lo[2 * m]);
+                        hpv_split_trunc(h1, hi[2 * m + 1], lo[2 * m + 1]);
+                    }
+                    hpv_tmem_st_n<HPH>(tb + lane_base + colAhi + ch * KP + u0, hi);
+                    hpv_tmem_st_n<HPH>(tb + lane_base + colAlo + ch * KP + u0, lo);
+                });
+                hpv_tmem_wait_st();
+                hpv_tc_fence_before();
+                __syncthreads();
+                if (warp == 0) {
+                    hpv_tc_fence_after();
+                    if (hpv_elect_one()) {
+                        const uint32_t bhi = hpv_smem_u32(s_B) + (uint32_t)(l - 1) * (uint32_t)(L.B_layer * 4);
+                        const uint32_t blo = bhi + (uint32_t)(KP * HPV_TC_NPAD * 4);
+                        if (TCOLS == 512u || tb == 0u) hpv_tc_issue_layer<0, NCH, KP>(bhi, blo, s_bar);
+                        else hpv_tc_issue_layer<256, NCH, KP>(bhi, blo, s_bar);
+                    }
+                    __syncwarp();
+                }
+            }
+            // output layer: partial sums over this thread's units, combined across the two halves
+            {
+                float acc[NCH];
+                hpv_each_ch<M>(s, [&](hpv_pair* hp_, int ch) {
+                    float sacc = 0.0f;
+#pragma unroll
+                    for (int m = 0; m < NPR; ++m) {
+                        float h0, h1;
+                        hpv_unpack(hp_[m], h0, h1);
+                        sacc = fmaf(h0, Wo[u0 + 2 * m], sacc);
+                        sacc = fmaf(h1, Wo[u0 + 2 * m + 1], sacc);
+                    }
+                    acc[ch] = sacc;
+                });
+                if (half == 1) {
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch) s_part[ch * HPV_TC_MTILE + prow] = acc[ch];
+                }
+                __syncthreads();
+                if (half == 0 && valid) {
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch) acc[ch] += s_part[ch * HPV_TC_MTILE + prow];
+                    float f[HPV_NFIELDS];
+                    f[0] = acc[M::C_V] + Wo[HP];
+                    f[1] = M::DX ? acc[M::DX ? M::C_DX : 0] : 0.0f;
+                    f[2] = M::DY ? acc[M::DY ? M::C_DY : 0] : 0.0f;
+                    f[3] = M::EX ? acc[M::EX ? M::C_EX : 0] : 0.0f;
+                    f[4] = M::EY ? acc[M::EY ? M::C_EY : 0] : 0.0f;
+#pragma unroll
+                    for (int t = 0; t < HPV_MAX_TERMS; ++t) {
+                        float g = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < HPV_NFIELDS; ++k) g = fmaf(coef[t][k], f[k], g);
+                        if (t < a.n_terms) s_G[t * L.GS + (p - base)] = g;
+                    }
+                }
+                if (nhid == 1) __syncthreads();       // otherwise the next tile's layer barriers protect s_part
+            }
+        }
+        hpv_sync(c);
+
+        // (3) first contraction, over the x index:  P_t[jl][r] = c_t * sum_i G_t[jl][i] * R_t[i][r]
+        {
+            const int ng = (nrows + 3) >> 2;
+            const int nitems = a.n_terms * ng * (HPV_NP / 4);
+            for (int item = tid; item < nitems; item += T) {
+                const int r4 = item & 15, rest = item >> 4;
+                const int g4 = rest % ng, t = rest / ng;
+                const int jl0 = 4 * g4;
+                const float* g0 = s_G + t * L.GS + (jl0 + 0 < nrows ? jl0 + 0 : nrows - 1) * Q;
+                const float* g1 = s_G + t * L.GS + (jl0 + 1 < nrows ? jl0 + 1 : nrows - 1) * Q;
+                const float* g2 = s_G + t * L.GS + (jl0 + 2 < nrows ? jl0 + 2 : nrows - 1) * Q;
+                const float* g3 = s_G + t * L.GS + (jl0 + 3 < nrows ? jl0 + 3 : nrows - 1) * Q;
+                const float* R = sm + L.tab[a.terms[t].rtab] + 4 * r4;
+                float acc[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+#pragma unroll 4
+                for (int i = 0; i < Q; ++i) {
+                    const HpvF4 w = hpv_ld4(R + i * HPV_NP);
+                    const float gv[4] = {g0[i], g1[i], g2[i], g3[i]};
+                    const float ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(gv[u], ws[v], acc[u][v]);
+                }
+                const float ct = hpv_term_scale(a.terms[t], hwx, hwy);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (jl0 + u < nrows) {
+                        HpvF4 o; o.x = ct * acc[u][0]; o.y = ct * acc[u][1]; o.z = ct * acc[u][2]; o.w = ct * acc[u][3];
+                        hpv_st4(s_P + (t * L.RMAX + jl0 + u) * HPV_NP + 4 * r4, o);
+                    }
+                }
+            }
+        }
+        hpv_sync(c);
+
+        // (4) second contraction, over the y index:  U[k][r] += sum_t sum_jl L_t[ja+jl][k] * P_t[jl][r]
+        for (int t = 0; t < a.n_terms; ++t) {
+            const float* Lt = sm + L.tab[a.terms[t].ltab] + ja * HPV_NP + 4 * kt;
+            const float* Pt = s_P + t * L.RMAX * HPV_NP + 4 * rt;
+#pragma unroll 4
+            for (int jl = 0; jl < nrows; ++jl) {
+                const HpvF4 l4 = hpv_ld4(Lt + jl * HPV_NP), p4 = hpv_ld4(Pt + jl * HPV_NP);
+                const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, ps[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) U[i][j] = fmaf(ls[i], ps[j], U[i][j]);
+            }
+        }
+
+        t_cur += nt;
+        if (t_cur == t_end || t_cur % tpe == 0) {
+            // (5) done with element e: publish the partial U; the last part to arrive reduces the parts in a fixed
+            // order, forms the residual and the element loss (as hpv_varfwd_body)
+            const int nparts = a.el_nparts[e];
+            const int slot = a.el_part_off[e] + (c.bid - a.el_first_cta[e]);
+            float* up = a.Upart + (size_t)slot * HPV_NP * HPV_NP;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                HpvF4 o; o.x = U[i][0]; o.y = U[i][1]; o.z = U[i][2]; o.w = U[i][3];
+                hpv_st4(up + (4 * kt + i) * HPV_NP + 4 * rt, o);
+                U[i][0] = U[i][1] = U[i][2] = U[i][3] = 0.0f;
+            }
+            hpv_fence();
+            hpv_sync(c);
+            if (tid == 0) {
+                unsigned int prev = hpv_atomic_inc(a.el_done + e);
+                s_flag[0] = (prev == (unsigned int)(nparts - 1)) ? 1 : 0;
+            }
+            hpv_sync(c);
+            if (s_flag[0]) {
+                hpv_fence();
+                const int ntx_e = a.el_ntest[2 * e + 0], nty_e = a.el_ntest[2 * e + 1];
+                float S[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) S[i][j] = 0.0f;
+                const float* base_p = a.Upart + (size_t)a.el_part_off[e] * HPV_NP * HPV_NP;
+#pragma unroll 4
+                for (int sp = 0; sp < nparts; ++sp) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        HpvF4 v = hpv_ld4_cg(base_p + (size_t)sp * HPV_NP * HPV_NP + (4 * kt + i) * HPV_NP + 4 * rt);
+                        S[i][0] += v.x; S[i][1] += v.y; S[i][2] += v.z; S[i][3] += v.w;
+                    }
+                }
+                float sq = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = 4 * kt + i;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = 4 * rt + j;
+                        if (k < nty_e && r < ntx_e) {
+                            const size_t idx = ((size_t)e * a.nty + k) * a.ntx + r;
+                            const float res = S[i][j] - (a.F ? a.F[idx] : 0.0f);
+                            a.Res[idx] = res;
+                            sq = fmaf(res, res, sq);
+                        } else if (k < a.nty && r < a.ntx) {
+                            a.Res[((size_t)e * a.nty + k) * a.ntx + r] = 0.0f;
+                        }
+                    }
+                }
+                const float tot = hpv_block_sum(c, s_red, sq);
+                if (tid == 0) {
+                    a.el_loss[e] = tot / (float)(ntx_e * nty_e);
+                    a.el_done[e] = 0u;
+                    hpv_fence();
+                    unsigned int prev = hpv_atomic_inc(a.n_done);
+                    s_flag[1] = (prev == (unsigned int)(a.n_el - 1)) ? 1 : 0;
+                }
+                hpv_sync(c);
+                if (s_flag[1]) {
+                    hpv_fence();
+                    double* dred = reinterpret_cast<double*>(s_red);
+                    double acc = 0.0;
+                    for (int i = tid; i < a.n_el; i += T) acc += (double)hpv_ld_cg(a.el_loss + i);
+                    dred[tid] = acc;
+                    hpv_sync(c);
+                    for (int sft = T >> 1; sft > 0; sft >>= 1) {
+                        if (tid < sft) dred[tid] += dred[tid + sft];
+                        hpv_sync(c);
+                    }
+                    if (tid == 0) { a.loss[0] = dred[0]; a.n_done[0] = 0u; }
+                }
+                hpv_sync(c);
+            }
+        }
+        hpv_sync(c);
+    }
+    hpv_pdl_trigger();
+    hpv_tc_fence_before();
+    __syncthreads();
+    if (warp == 0) hpv_tmem_dealloc(tb, TCOLS);
+}
+
+#endif  // __CUDACC__

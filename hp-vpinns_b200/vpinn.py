@@ -124,10 +124,52 @@ class _VPINNBase:
         self.train_op_Adam = _Fetch("train_op_Adam")
         self.epsilon = _Fetch("epsilon")
 
+    # ---- multi-GPU (one process per GPU, element shards) -------------------------------------------
+    def _init_sharding(self, elements, owns_point_losses):
+        """The point-wise losses (boundary data, PINN residual) are REPLICATED data: in a sharded run exactly one
+        rank may add them to the exchanged sum, or the objective silently becomes world_size * lossb + lossv.
+        owns_point_losses=None: rank 0 of the default process group when `elements` is a shard and torch.distributed
+        is initialised, else True."""
+        self._dist = None
+        if owns_point_losses is None:
+            owns_point_losses = True
+            if elements is not None:
+                try:
+                    import torch.distributed as dist
+                    if dist.is_available() and dist.is_initialized():
+                        owns_point_losses = dist.get_rank() == 0
+                except ImportError:
+                    pass
+        self.owns_point_losses = bool(owns_point_losses)
+
+    def _point_slots(self, slots):
+        return tuple(slots) if self.owns_point_losses else ()
+
+    def attach_distributed(self, group=None):
+        """Connect this rank's engine with its peers (hpv_peer_export / hpv_peer_connect): from here on
+        train() sums gradient and losses over the ranks inside the step's last kernel, and every loss this class
+        reads back is the GLOBAL value (so that `loss < tresh` stops all ranks at the same iteration)."""
+        import torch.distributed as dist
+        from .distributed import connect_peers
+        if connect_peers(self.engine, group):
+            self._dist = (dist, group)
+        return self._dist is not None
+
     def _losses(self):
-        """One evaluation of every loss at the current parameters (no update): dict of floats."""
+        """One evaluation of every loss at the current parameters (no update): dict of floats.  In a sharded run
+        the values are summed over the ranks (each rank evaluates its element block; the point losses are added by
+        their owner only)."""
         self.engine.loss_and_grad()
         v = self.engine.read_losses()
+        if getattr(self, "_dist", None) is not None:
+            import torch
+            dist, group = self._dist
+            backend = dist.get_backend(group)
+            t = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64))
+            if backend == "nccl":
+                t = t.cuda()
+            dist.all_reduce(t, group=group)
+            v = t.cpu().numpy()
         return self._name_losses(v)
 
     def _fetch(self, name):
@@ -174,7 +216,7 @@ class VPINN_Poisson2D(_VPINNBase):
 
     def __init__(self, X_u_train, u_train, X_f_train, f_train, X_quad, W_quad, U_exact_total, F_exact_total,
                  gridx, gridy, N_testfcn, X_test, u_test, layers, var_form=None, scheme=None, loss_his=None,
-                 device=0, seed=1234, elements=None):
+                 device=0, seed=1234, elements=None, owns_point_losses=None):
         self.var_form = _from_caller("var_form", var_form, 1)
         self.scheme = _from_caller("scheme", scheme, "VPINNs")
         self.loss_his = _from_caller("loss_his", loss_his, None)
@@ -200,14 +242,14 @@ class VPINN_Poisson2D(_VPINNBase):
         if elements is not None:                 # element shard of this rank (multi-GPU)
             lo, hi, nt, F = lo[elements], hi[elements], nt[elements], F[elements]
         self._setup_engine(device, self.layers, xi, w, max(ntx, nty), lo, hi, ntx, nty, F, nt, self.var_form)
-        self._has_boundary = elements is None or getattr(elements, "owns_point_losses", True)
+        self._init_sharding(elements, owns_point_losses)
         e = self.engine
         e.set_point_loss(0, X_u_train, self.utrain, [1, 0, 0, 0, 0], None, 10.0)          # 10*lossb (P2D:125-128)
         e.set_point_loss(1, X_f_train, self.ftrain, [0, 0, 0, 1, 1], None, 1.0)           # lossp (P2D:123, 187-194)
         if self.scheme == "VPINNs":
-            e.configure_training(wv=1.0, point_slots=(0,), lr=0.001)
+            e.configure_training(wv=1.0, point_slots=self._point_slots((0,)), lr=0.001)
         elif self.scheme == "PINNs":
-            e.configure_training(wv=0.0, point_slots=(0, 1), lr=0.001)
+            e.configure_training(wv=0.0, point_slots=self._point_slots((0, 1)), lr=0.001)
         else:
             raise ValueError("scheme must be 'VPINNs' or 'PINNs' (P2D:125-128)")
         self.u_test = _Fetch("u_test")
@@ -283,7 +325,7 @@ class VPINN_Poisson1D(_VPINNBase):
 
     def __init__(self, X_u_train, u_train, X_quad, W_quad, F_exact_total, grid, X_test, u_test, layers, X_f_train,
                  f_train, var_form=None, lossb_weight=None, LR=None, total_record=None, device=0, seed=1234,
-                 elements=None):
+                 elements=None, owns_point_losses=None):
         self.var_form = _from_caller("var_form", var_form, 1)
         self.lossb_weight = _from_caller("lossb_weight", lossb_weight, 1)
         self.LR = _from_caller("LR", LR, 0.001)
@@ -308,12 +350,13 @@ class VPINN_Poisson1D(_VPINNBase):
             lo, hi, F = lo[elements], hi[elements], F[elements]
         self._setup_engine(device, self.layers, self.xquad.ravel(), self.wquad.ravel(), self.N_test, lo, hi, self.N_test, 1,
                            F, None, self.var_form)
+        self._init_sharding(elements, owns_point_losses)
         e = self.engine
         slots = ()
         if self.lossb_weight != 0:
             e.set_point_loss(0, self.x, self.u, [1, 0, 0, 0, 0], None, float(self.lossb_weight))   # P1D:98-100
             slots = (0,)
-        e.configure_training(wv=1.0, point_slots=slots, lr=float(self.LR))
+        e.configure_training(wv=1.0, point_slots=self._point_slots(slots), lr=float(self.LR))
 
     def _name_losses(self, v):
         lb = v[2] / self.lossb_weight if self.lossb_weight != 0 else float("nan")
@@ -370,7 +413,8 @@ class VPINN_AdvDiff(_VPINNBase):
     PROBLEM = "advdiff"
 
     def __init__(self, XT_u_train, u_train, XT_f_train, XT_quad, W_quad, T_quad, WT_quad, grid_x, grid_t, N_testfcn,
-                 XT_test, u_test, layers, lb, ub, var_form=None, V=None, LR=None, device=0, seed=1234, elements=None):
+                 XT_test, u_test, layers, lb, ub, var_form=None, V=None, LR=None, device=0, seed=1234, elements=None,
+                 owns_point_losses=None):
         self.var_form = _from_caller("var_form", var_form, 0)
         self.V = _from_caller("V", V, 1.0)
         self.LR = _from_caller("LR", LR, 0.001)
@@ -394,11 +438,12 @@ class VPINN_AdvDiff(_VPINNBase):
         if elements is not None:
             lo, hi, nt = lo[elements], hi[elements], nt[elements]
         self._setup_engine(device, self.layers, xi, w, max(ntx, ntt), lo, hi, ntx, ntt, None, nt, self.var_form, float(self.V))
+        self._init_sharding(elements, owns_point_losses)
         e = self.engine
         e.set_point_loss(0, XT_u_train, self.u, [1, 0, 0, 0, 0], None, 10.0)                 # lossb = 10*mean(.) (ADI:184)
         # strong-form residual u_t + V u_x - eps u_xx against 0 (net_f, ADI:247-253; lossp, ADI:186 -- not in the loss)
         e.set_point_loss(1, XT_f_train, np.zeros(XT_f_train.shape[0]), [0, float(self.V), 1, 0, 0], [0, 0, 0, -1, 0], 1.0)
-        e.configure_training(wv=1.0, point_slots=(0,), train_eps=True, lr=float(self.LR))
+        e.configure_training(wv=1.0, point_slots=self._point_slots((0,)), train_eps=True, lr=float(self.LR))
         self.u_NN_test = _Fetch("u_NN_test")
 
     def _name_losses(self, v):
