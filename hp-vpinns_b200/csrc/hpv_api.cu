@@ -106,6 +106,8 @@ struct hpv_ctx {
     double adam_t = 0.0;                               // host copy of the optimizer's step counter
     bool fwd_tc = true;                // forward kernel in its tensor-core form (HPV_FWD_TC=0: the FP32-FFMA form)
     bool fwd_tc_active = false;        // ... and the current network / form / rule admit it (decided by ensure_ready)
+    bool bwd_tc = true;                // reverse sweep in its tensor-core form (HPV_BWD_TC=0: the FP32-FFMA form)
+    bool bwd_tc_active = false;
     int fwd_ctas_per_sm = 0, adj_grid = 0, slabs_per_el = 0;
     PointSet ps[HPV_MAX_POINT_SETS];
     // training configuration
@@ -356,6 +358,32 @@ int ensure_ready(hpv_ctx* c) {
     const long long npts = (long long)c->n_el * rows * c->Q;
     { int r = plan_bwd(c, bwd_key_of(c), npts, c->bwd_block, c->bwd_grid, c->bwd_smem); if (r) return r; }
     c->bwd_ctas_per_sm = (c->bwd_grid + c->n_sm - 1) / c->n_sm;
+    c->bwd_tc_active = false;
+    {
+        // tensor-core form of the reverse sweep (hpv_varbwd_tc.cuh) when its TMEM / shared-memory plan fits
+        const HpvKernelKey kb = bwd_key_of(c);
+        const int nch_b = kb.dir ? 2 : hpv_mode_nch(kb.dim, kb.mx, kb.my);
+        if (c->bwd_tc && hpv_tc_supported(nch_b, kb.hp)) {
+            HpvVarArgs va; memset(&va, 0, sizeof(va));
+            va.nhid = c->net.nhid;
+            HpvBwdArgs bb; memset(&bb, 0, sizeof(bb)); bb.v = va;
+            HpvLaunch l; memset(&l, 0, sizeof(l));
+            long long out = 0;
+            l.kind = HPV_K_MLPBWD_TC; l.bwd = &bb; l.out = &out; l.op = 2; l.block = HPV_THREADS;
+            HPV_CK(hpv_dispatch(kb, l));
+            const size_t sm_tc = (size_t)out;
+            if (sm_tc <= 227 * 1024) {
+                l.op = 1; l.smem = sm_tc;
+                HPV_CK(hpv_dispatch(kb, l));
+                if (out >= 1) {
+                    const long long n_tiles = (npts + HPV_TC_MTILE - 1) / HPV_TC_MTILE;
+                    const long long slots = (long long)c->n_sm * out;
+                    c->bwd_tc_active = true; c->bwd_smem = sm_tc; c->bwd_block = HPV_THREADS; c->bwd_ctas_per_sm = (int)out;
+                    c->bwd_grid = (int)(n_tiles < slots ? (n_tiles < 1 ? 1 : n_tiles) : slots);
+                }
+            }
+        }
+    }
     { int r = ensure_grad_buffers(c, c->bwd_grid); if (r) return r; }
     HPV_CK(c->Gbar.alloc((size_t)c->form.n_terms * npts));
     c->slabs_per_el = (rows + HPV_ADJ_RS - 1) / HPV_ADJ_RS;
@@ -387,14 +415,15 @@ int launch_adjproj(hpv_ctx* c) {
 }
 
 int launch_mlpbwd_var(hpv_ctx* c) {
-    { int r = refresh_mirror(c, HPV_K_MLPBWD); if (r) return r; }
+    // the tensor-core form reads the parameters from global memory (theta_pad), not from the constant-memory mirror
+    if (!c->bwd_tc_active) { int r = refresh_mirror(c, HPV_K_MLPBWD); if (r) return r; }
     HpvBwdArgs ba; fill_var_args(c, ba.v);
     const int rows = (c->net.dim == 2) ? c->Q : 1;
     ba.Gbar = c->Gbar.p; ba.n_points = c->n_el * rows * c->Q;
     ba.pts = nullptr;
     ba.stagger_ns = c->bwd_stagger_ns;
     HpvLaunch l; memset(&l, 0, sizeof(l));
-    l.kind = HPV_K_MLPBWD; l.op = 0; l.grid = c->bwd_grid; l.block = c->bwd_block; l.smem = c->bwd_smem;
+    l.kind = c->bwd_tc_active ? HPV_K_MLPBWD_TC : HPV_K_MLPBWD; l.op = 0; l.grid = c->bwd_grid; l.block = c->bwd_block; l.smem = c->bwd_smem;
     l.stream = c->stream; l.bwd = &ba;
     HPV_CK(hpv_dispatch(bwd_key_of(c), l));
     c->launches += 1;
@@ -527,6 +556,7 @@ int hpv_create(hpv_ctx** out, int device) {
     if (const char* ev = getenv("HPV_ADAM_DIRECT")) ctx->adam_direct = atoi(ev) != 0;
     if (const char* ev = getenv("HPV_FWD_TC")) ctx->fwd_tc = atoi(ev) != 0;
     if (const char* ev = getenv("HPV_GRAPH")) ctx->use_graph = atoi(ev) != 0;
+    if (const char* ev = getenv("HPV_BWD_TC")) ctx->bwd_tc = atoi(ev) != 0;
     if (const char* ev = getenv("HPV_BWD_STAGGER_NS")) ctx->bwd_stagger_ns = atoi(ev);
     if (const char* ev = getenv("HPV_PEER_TIMEOUT_S")) { const double v = atof(ev); if (v > 0) ctx->peer_timeout_ns = (unsigned long long)(v * 1e9); }
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
@@ -1285,10 +1315,10 @@ int hpv_kernel_info(hpv_ctx* c, int* info, int n) {
     if (!c || !info) return HPV_ERR_ARG;
     HPV_CK(cudaSetDevice(c->device));
     { int r = ensure_ready(c); if (r) return r; }
-    const int v[14] = {c->n_sm, c->part.n_ctas, HPV_THREADS, (int)c->fwd_smem, c->fwd_ctas_per_sm,
+    const int v[15] = {c->n_sm, c->part.n_ctas, HPV_THREADS, (int)c->fwd_smem, c->fwd_ctas_per_sm,
                        c->bwd_grid, c->bwd_block, (int)c->bwd_smem, c->bwd_ctas_per_sm,
-                       c->adj_grid, (int)c->adj_smem, c->net.hp, bwd_key_of(c).dir, c->fwd_tc_active ? 1 : 0};
-    for (int i = 0; i < n && i < 14; ++i) info[i] = v[i];
+                       c->adj_grid, (int)c->adj_smem, c->net.hp, bwd_key_of(c).dir, c->fwd_tc_active ? 1 : 0, c->bwd_tc_active ? 1 : 0};
+    for (int i = 0; i < n && i < 15; ++i) info[i] = v[i];
     return HPV_OK;
 }
 

@@ -26,6 +26,42 @@ hpv_varfwd_tc_kernel(const __grid_constant__ HpvVarArgs a) {
     if constexpr (hpv_tc_supported(HpvMode<DIM, MX, MY>::NCH, HP)) hpv_varfwd_tc_body<DIM, MX, MY, HP, ACT>(c, a);
 }
 
+// Tensor-core form of the reverse sweep (hpv_varbwd_tc.cuh).
+template <int DIM, int MX, int MY, int HP, int ACT>
+__global__ void __launch_bounds__(HPV_THREADS, (hpv_tc_tmem_need(HpvMode<DIM, MX, MY>::NCH, HP) <= 256 ? 2 : 1))
+hpv_mlpbwd_tc_kernel(const __grid_constant__ HpvBwdArgs a) {
+    extern __shared__ __align__(128) unsigned char hpv_smem_tcb[];
+    HpvCta c;
+    c.tid = threadIdx.x; c.nthreads = blockDim.x; c.bid = blockIdx.x; c.nblocks = gridDim.x;
+    c.smem = hpv_smem_tcb; c.emu = nullptr;
+    if constexpr (hpv_tc_supported(HpvMode<DIM, MX, MY>::NCH, HP)) hpv_mlpbwd_tc_body<DIM, MX, MY, HP, ACT>(c, a);
+}
+
+// Resident CTAs per SM of a tensor-core kernel from its resources.  (cudaOccupancyMaxActiveBlocksPerMultiprocessor
+// answered 1 for the 89 KB / 128-register headline instance of the forward kernel although the hardware co-schedules
+// two -- ncu: block limit registers 2, shared memory 2 -- so the bound is computed here; nothing depends on
+// co-residency for correctness, the figure only sizes the persistent grid.)
+template <typename K>
+static cudaError_t hpv_tc_resident(K k, int block, size_t smem, int nch, int hp, long long* out) {
+    int n = 0;
+    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, block, smem);
+    if (err != cudaSuccess) return err;
+    cudaFuncAttributes fa;
+    if ((err = cudaFuncGetAttributes(&fa, k)) != cudaSuccess) return err;
+    int dev = 0, smem_sm = 0, regs_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+    const int regs_cta = ((fa.numRegs * 32 + 255) / 256) * 256 * (block / 32);
+    const int by_regs = regs_cta > 0 ? regs_sm / regs_cta : 1;
+    const int by_smem = (int)((size_t)smem_sm / (smem + fa.sharedSizeBytes + 1024));
+    const int own = by_regs < by_smem ? by_regs : by_smem;
+    if (n < own) n = own;
+    const int by_tmem = 512 / hpv_tc_tmem_cols(nch, hp);
+    *out = n < by_tmem ? n : by_tmem;
+    return cudaSuccess;
+}
+
 // Launch bounds of the reverse sweep.  The host picks the number of warps per SM and their grouping into CTAs per
 // launch (plan_bwd): the warps share nothing but the constant parameters, so a CTA is only a resource container.
 // The kernel is bound by shared-memory / constant-load latency, so resident warps matter more than registers:
@@ -100,13 +136,24 @@ static cudaError_t hpv_do(const HpvLaunch& l) {
             auto k = hpv_varfwd_tc_kernel<DIM, MX, MY, HP, ACT>;
             if ((err = hpv_prepare(k, l.smem, prepared)) != cudaSuccess) return err;
             if (l.op == 1) {
-                int n = 0;
-                err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, l.block, l.smem);
-                const int by_tmem = 512 / hpv_tc_tmem_cols(HpvMode<DIM, MX, MY>::NCH, HP);
-                *l.out = n < by_tmem ? n : by_tmem;
-                return err;
+                return hpv_tc_resident(k, l.block, l.smem, HpvMode<DIM, MX, MY>::NCH, HP, l.out);
             }
             k<<<l.grid, l.block, l.smem, l.stream>>>(*l.var);
+        }
+    } else if constexpr (KIND == HPV_K_MLPBWD_TC) {
+        if constexpr (!hpv_tc_supported(HpvMode<DIM, MX, MY>::NCH, HP)) {
+            return cudaErrorInvalidValue;
+        } else {
+            auto k = hpv_mlpbwd_tc_kernel<DIM, MX, MY, HP, ACT>;
+            if (l.op == 2) {
+                typedef HpvMode<DIM, MX, MY> M;
+                const HpvBwdTcSmem L = hpv_bwd_tc_smem(DIM, HP, M::NCH, 1 + (M::DX ? 1 : 0) + (M::DY ? 1 : 0), l.bwd->v.nhid);
+                *l.out = (long long)L.total * 4;
+                return cudaSuccess;
+            }
+            if ((err = hpv_prepare(k, l.smem, prepared)) != cudaSuccess) return err;
+            if (l.op == 1) return hpv_tc_resident(k, l.block, l.smem, HpvMode<DIM, MX, MY>::NCH, HP, l.out);
+            return hpv_launch_pdl(k, l.grid, l.block, l.smem, l.stream, *l.bwd);
         }
     } else if constexpr (KIND == HPV_K_MLPBWD) {
         auto k = hpv_mlpbwd_kernel<DIM, MX, MY, HP, ACT>;
@@ -162,7 +209,7 @@ static cudaError_t hpv_dispatch_hp(const HpvKernelKey& k, const HpvLaunch& l) {
         return hpv_do_act<1, 2, 0, HP, KIND>(k, l);
     }
     if (k.mx == 0 && k.my == 0) return hpv_do_act<2, 0, 0, HP, KIND>(k, l);
-    if constexpr (KIND == HPV_K_MLPBWD) {
+    if constexpr (KIND == HPV_K_MLPBWD || KIND == HPV_K_MLPBWD_TC) {
         if (k.dir && k.mx <= 1 && k.my <= 1) return hpv_do_act<2, 1, 0, HP, KIND>(k, l);
     }
     if (k.mx <= 1 && k.my <= 1) return hpv_do_act<2, 1, 1, HP, KIND>(k, l);

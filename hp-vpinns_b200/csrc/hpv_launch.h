@@ -6,6 +6,7 @@
 #include "hpv_varbwd.cuh"
 #include "hpv_points.cuh"
 #include "hpv_varfwd_tc.cuh"
+#include "hpv_varbwd_tc.cuh"
 
 // dir != 0 (reverse sweep only): the directional mode HpvMode<2, 1, 0> instead of <2, 1, 1>.
 // Launch with programmatic stream serialisation: the kernel's CTAs may start before the previous kernel of the
@@ -32,7 +33,7 @@ inline cudaError_t hpv_launch_pdl(void (*kernel)(KArgs...), int grid, int block,
 
 struct HpvKernelKey { int dim, mx, my, hp, act, dir; };
 
-enum { HPV_K_VARFWD = 0, HPV_K_MLPBWD = 1, HPV_K_POINTS = 2, HPV_K_VARFWD_TC = 3 };
+enum { HPV_K_VARFWD = 0, HPV_K_MLPBWD = 1, HPV_K_POINTS = 2, HPV_K_VARFWD_TC = 3, HPV_K_MLPBWD_TC = 4 };
 
 // op: 0 = launch, 1 = query resident CTAs per SM for (block, smem) into *out, 4 = (reverse sweep) the largest
 // block size the kernel was compiled for, 2 = shared memory bytes of the
@@ -54,7 +55,8 @@ struct HpvLaunch {
     cudaError_t hpv_dispatch_h##hp##_fwd(const HpvKernelKey& k, const HpvLaunch& l); \
     cudaError_t hpv_dispatch_h##hp##_bwd(const HpvKernelKey& k, const HpvLaunch& l); \
     cudaError_t hpv_dispatch_h##hp##_pts(const HpvKernelKey& k, const HpvLaunch& l); \
-    cudaError_t hpv_dispatch_h##hp##_fwdtc(const HpvKernelKey& k, const HpvLaunch& l);
+    cudaError_t hpv_dispatch_h##hp##_fwdtc(const HpvKernelKey& k, const HpvLaunch& l); \
+    cudaError_t hpv_dispatch_h##hp##_bwdtc(const HpvKernelKey& k, const HpvLaunch& l);
 HPV_DECL(8)
 HPV_DECL(20)
 HPV_DECL(32)
@@ -66,6 +68,7 @@ inline cudaError_t hpv_dispatch(const HpvKernelKey& k, const HpvLaunch& l) {
         if (l.kind == HPV_K_VARFWD) return hpv_dispatch_h##hpv##_fwd(k, l); \
         if (l.kind == HPV_K_MLPBWD) return hpv_dispatch_h##hpv##_bwd(k, l); \
         if (l.kind == HPV_K_VARFWD_TC) return hpv_dispatch_h##hpv##_fwdtc(k, l); \
+        if (l.kind == HPV_K_MLPBWD_TC) return hpv_dispatch_h##hpv##_bwdtc(k, l); \
         return hpv_dispatch_h##hpv##_pts(k, l); \
     }
     HPV_CASE(8)

@@ -202,7 +202,9 @@ struct HpvBwdSmem {
 // shared memory; nothing here synchronises with other warps.
 //   KIND 0: hidden layer, D = W[HP][HP], bias row -> b (= W + HP*HP).   KIND 1: output layer, D = Wo[HP] followed
 //   by (bo, 0, 0, 0), TN = 1.   KIND 2: first layer, IN rows = (x, y, 1, 0): rows < DIM -> W1, row 2 -> b1.
-template <int SPI, int SPA, int NCH, int NROWS, int NJ, int TN, bool BIAS, int KIND, int HP, int DIM>
+// NPTS points per call (32: a whole warp tile; 16: half of it -- the tensor-core reverse sweep shares a tile between two
+// warps), CHS rows between the channel blocks of IN / ADJ.
+template <int SPI, int SPA, int NCH, int NROWS, int NJ, int TN, bool BIAS, int KIND, int HP, int DIM, int NPTS = 32, int CHS = 32>
 HPV_HD void hpv_wgrad_warp(const HpvCta& c, const float* IN, const float* ADJ, float* D, float* Db, const float* cst) {
     constexpr int NI = (NROWS + (BIAS ? 1 : 0) + 3) / 4;
     constexpr int NTILES = NI * NJ;
@@ -224,11 +226,12 @@ HPV_HD void hpv_wgrad_warp(const HpvCta& c, const float* IN, const float* ADJ, f
         if (active) {
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
-                const float* pa = (ty == 0) ? IN + (ch * 32 + ks) * SPI + r0 : ((ty == 1 && ch == 0) ? cst : cst + 4);
+                const float* pa = (ty == 0) ? IN + (ch * CHS + ks) * SPI + r0 : ((ty == 1 && ch == 0) ? cst : cst + 4);
                 const int sa = (ty == 0) ? KSW * SPI : 0;
-                const float* pb = ADJ + (ch * 32 + ks) * SPA + (TN == 4 ? 4 * jt : 0);
+                const float* pb = ADJ + (ch * CHS + ks) * SPA + (TN == 4 ? 4 * jt : 0);
+                static_assert(NPTS % KSW == 0, "points per call must be a multiple of the K split");
 #pragma unroll 8
-                for (int k = 0; k < 32 / KSW; ++k) {
+                for (int k = 0; k < NPTS / KSW; ++k) {
                     const HpvF4 a4 = hpv_ld4(pa);
                     pa += sa;
                     if constexpr (TN == 4) {

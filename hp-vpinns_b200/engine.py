@@ -235,10 +235,10 @@ class Engine:
         return int(self._lib.hpv_launch_count(self._h))
 
     def kernel_info(self):
-        v = np.zeros(14, dtype=np.int32)
+        v = np.zeros(15, dtype=np.int32)
         self._ck(self._lib.hpv_kernel_info(self._h, L.iptr(v), v.size))
         keys = ["n_sm", "fwd_grid", "fwd_block", "fwd_smem", "fwd_ctas_per_sm", "bwd_grid", "bwd_block", "bwd_smem",
-                "bwd_ctas_per_sm", "adj_grid", "adj_smem", "hidden_pad", "bwd_directional", "fwd_tensor_core"]
+                "bwd_ctas_per_sm", "adj_grid", "adj_smem", "hidden_pad", "bwd_directional", "fwd_tensor_core", "bwd_tensor_core"]
         return dict(zip(keys, (int(x) for x in v)))
 
     def probe_fp32_peak(self, variant=0):

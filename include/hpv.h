@@ -133,9 +133,10 @@ int hpv_reset_optimizer(hpv_ctx* ctx);
 int hpv_train_steps(hpv_ctx* ctx, int nsteps, double* loss_history);
 
 /* Measurement helpers for bench.py: launch counter of this context, the dominant kernels' launch geometry
- * (info[0..13] = SMs, forward grid/block/smem/CTAs per SM, reverse-sweep grid/block/smem/CTAs per SM, adjoint
+ * (info[0..14] = SMs, forward grid/block/smem/CTAs per SM, reverse-sweep grid/block/smem/CTAs per SM, adjoint
  * projection grid/smem, padded hidden width, 1 if the reverse sweep runs in the directional mode, 1 if the forward
- * kernel runs in its tensor-core form (tcgen05 layer products, TMA-staged tables; HPV_FWD_TC=0 selects the FFMA form)),
+ * kernel runs in its tensor-core form (tcgen05 layer products, TMA-staged tables; HPV_FWD_TC=0 selects the FFMA form), the same for the
+ * reverse sweep (HPV_BWD_TC=0)),
  * and the FP32-FFMA probe (variant 0 register operands, 1 constant-bank operand, 2 packed f32x2); the probe
  * returns the achieved TFLOP/s measured with CUDA events on the context's stream. */
 long long hpv_launch_count(hpv_ctx* ctx);

@@ -37,7 +37,9 @@ def test_c3_near_converged_theta_matches_float64_fixture():
     if not os.path.exists(path):
         pytest.skip("fixture c3_converged.npz not generated yet (tests/golden/make_converged_theta.py)")
     fx = dict(np.load(path))
-    assert fx["lossv"] < 1e-3 * fx["lossv_initial"]                     # the fixture is in the cancelling regime
+    # the fixture is in the cancelling regime: lossv fell to < 1 % of its initial value, max|Res| ~ 9 % of max|F|
+    # (L-BFGS on the steep tanh(10 x) solution stalls there; the deeper regime is test_c3_deep_cancellation below)
+    assert fx["lossv"] < 1e-2 * fx["lossv_initial"]
     g = np.linspace(-1, 1, int(fx["ne"]) + 1)
     inp, X, W, F = _poisson2d_inputs(g, g, int(fx["Q"]), int(fx["N"]), fx["theta"], [int(v) for v in fx["layers"]], 1)
     eng = G.make_engine(inp)
@@ -52,6 +54,34 @@ def test_c3_near_converged_theta_matches_float64_fixture():
     assert np.abs(got - ref).max() <= 2e-5 * float(fx["F_max"])
     assert np.abs(got - ref).max() <= 2e-3 * np.abs(ref).max()
     assert np.abs(grad - fx["grad"]).max() <= 1e-4 * np.abs(fx["grad"]).max()
+    eng.close()
+
+
+def test_c3_deep_cancellation_reaches_the_fp32_floor():
+    """Deeper than training gets in minutes: the right-hand side is set to F' = U(theta) - delta with |delta| = 1e-3 max|F|,
+    so that U and F' cancel to three digits.  In fp32 the residual then carries the rounding of U itself
+    (~1e-7 |U|): the stated bound is an ABSOLUTE residual error of 2e-6 max|F| -- the same bound the other tests
+    state relative to the largest entry -- and lossv within 2 * that / rms(delta)."""
+    path = os.path.join(C.GOLDEN, "c3_converged.npz")
+    if not os.path.exists(path):
+        pytest.skip("fixture c3_converged.npz not generated yet")
+    fx = dict(np.load(path))
+    layers = [int(v) for v in fx["layers"]]
+    g = np.linspace(-1, 1, int(fx["ne"]) + 1)
+    inp, X, W, F = _poisson2d_inputs(g, g, int(fx["Q"]), int(fx["N"]), fx["theta"], layers, 1)
+    Ws, bs = O.unpack_theta(fx["theta"], layers)
+    r_ref = O.varloss_2d_factorised(Ws, bs, X, W, F, g, g, 60, 60, 1)[1].numpy().reshape(64, 60, 60)
+    U_ref = r_ref + F.reshape(64, 60, 60)
+    Fmax = np.abs(F).max()
+    k, r = np.meshgrid(np.arange(60), np.arange(60), indexing="ij")
+    delta = 1e-3 * Fmax * np.cos(0.37 * k + 0.11 * r)[None] * (1 + 0.01 * np.arange(64))[:, None, None]
+    inp2 = dict(inp, F=U_ref - delta)
+    eng = G.make_engine(inp2)
+    loss, res = eng.varloss_forward()
+    err = np.abs(res - delta).max()
+    assert err <= 2e-6 * Fmax
+    l_ref = float(np.sum(np.mean(delta.reshape(64, -1) ** 2, axis=1)))
+    assert loss == pytest.approx(l_ref, rel=2 * 2e-6 * Fmax / np.sqrt(np.mean(delta ** 2)))
     eng.close()
 
 
