@@ -106,8 +106,14 @@ struct hpv_ctx {
     double adam_t = 0.0;                               // host copy of the optimizer's step counter
     bool fwd_tc = true;                // forward kernel in its tensor-core form (HPV_FWD_TC=0: the FP32-FFMA form)
     bool fwd_tc_active = false;        // ... and the current network / form / rule admit it (decided by ensure_ready)
-    bool bwd_tc = true;                // reverse sweep in its tensor-core form (HPV_BWD_TC=0: the FP32-FFMA form)
+    // Reverse sweep in its tensor-core form (hpv_varbwd_tc.cuh): -1 = automatic (small batches only: below ~2 warp
+    // tiles per SM the FFMA sweep cannot fill the machine and the tensor-core form is 2x faster, C2: 23 vs 47 us; on
+    // large batches the FFMA sweep is still the faster one, C3: 133 vs 152 us), HPV_BWD_TC=0/1 forces it off/on
+    int bwd_tc = -1;
     bool bwd_tc_active = false;
+    bool bwd_tcw = false;              // ... with the weight gradients on the tensor cores too (HPV_BWD_TCW=1; measured slower and
+                                       // less accurate than the FMA-pipe weight gradients: DESIGN.md, kept for A/B measurements)
+    bool bwd_tcw_active = false;
     int fwd_ctas_per_sm = 0, adj_grid = 0, slabs_per_el = 0;
     PointSet ps[HPV_MAX_POINT_SETS];
     // training configuration
@@ -153,7 +159,7 @@ int upload(hpv_ctx* c, DevBuf<T>& b, const std::vector<T>& h) {
 
 HpvKernelKey key_of(const hpv_ctx* c, int mx, int my) {
     HpvKernelKey k;
-    k.dim = c->net.dim; k.mx = mx; k.my = my; k.hp = c->net.hp; k.act = c->net.act; k.dir = 0;
+    k.dim = c->net.dim; k.mx = mx; k.my = my; k.hp = c->net.hp; k.act = c->net.act; k.dir = 0; k.wg = 0;
     hpv_canon_mode(k.dim, k.mx, k.my);
     return k;
 }
@@ -358,18 +364,23 @@ int ensure_ready(hpv_ctx* c) {
     const long long npts = (long long)c->n_el * rows * c->Q;
     { int r = plan_bwd(c, bwd_key_of(c), npts, c->bwd_block, c->bwd_grid, c->bwd_smem); if (r) return r; }
     c->bwd_ctas_per_sm = (c->bwd_grid + c->n_sm - 1) / c->n_sm;
-    c->bwd_tc_active = false;
+    c->bwd_tc_active = false; c->bwd_tcw_active = false;
     {
         // tensor-core form of the reverse sweep (hpv_varbwd_tc.cuh) when its TMEM / shared-memory plan fits
         const HpvKernelKey kb = bwd_key_of(c);
         const int nch_b = kb.dir ? 2 : hpv_mode_nch(kb.dim, kb.mx, kb.my);
-        if (c->bwd_tc && hpv_tc_supported(nch_b, kb.hp)) {
+        const bool want_tc = c->bwd_tc == 1 || (c->bwd_tc < 0 && npts <= (long long)64 * c->n_sm);
+        if (want_tc && hpv_tc_supported(nch_b, kb.hp)) {
             HpvVarArgs va; memset(&va, 0, sizeof(va));
             va.nhid = c->net.nhid;
             HpvBwdArgs bb; memset(&bb, 0, sizeof(bb)); bb.v = va;
             HpvLaunch l; memset(&l, 0, sizeof(l));
             long long out = 0;
-            l.kind = HPV_K_MLPBWD_TC; l.bwd = &bb; l.out = &out; l.op = 2; l.block = HPV_THREADS;
+            l.kind = HPV_K_MLPBWD_TC; l.bwd = &bb; l.out = &out; l.block = HPV_THREADS; l.wg = c->bwd_tcw ? 1 : 0;
+            l.op = 5;
+            HPV_CK(hpv_dispatch(kb, l));
+            c->bwd_tcw_active = out != 0;
+            l.op = 2;
             HPV_CK(hpv_dispatch(kb, l));
             const size_t sm_tc = (size_t)out;
             if (sm_tc <= 227 * 1024) {
@@ -424,7 +435,7 @@ int launch_mlpbwd_var(hpv_ctx* c) {
     ba.stagger_ns = c->bwd_stagger_ns;
     HpvLaunch l; memset(&l, 0, sizeof(l));
     l.kind = c->bwd_tc_active ? HPV_K_MLPBWD_TC : HPV_K_MLPBWD; l.op = 0; l.grid = c->bwd_grid; l.block = c->bwd_block; l.smem = c->bwd_smem;
-    l.stream = c->stream; l.bwd = &ba;
+    l.stream = c->stream; l.bwd = &ba; l.wg = c->bwd_tcw ? 1 : 0;
     HPV_CK(hpv_dispatch(bwd_key_of(c), l));
     c->launches += 1;
     return HPV_OK;
@@ -556,7 +567,8 @@ int hpv_create(hpv_ctx** out, int device) {
     if (const char* ev = getenv("HPV_ADAM_DIRECT")) ctx->adam_direct = atoi(ev) != 0;
     if (const char* ev = getenv("HPV_FWD_TC")) ctx->fwd_tc = atoi(ev) != 0;
     if (const char* ev = getenv("HPV_GRAPH")) ctx->use_graph = atoi(ev) != 0;
-    if (const char* ev = getenv("HPV_BWD_TC")) ctx->bwd_tc = atoi(ev) != 0;
+    if (const char* ev = getenv("HPV_BWD_TC")) ctx->bwd_tc = atoi(ev) != 0 ? 1 : 0;
+    if (const char* ev = getenv("HPV_BWD_TCW")) ctx->bwd_tcw = atoi(ev) != 0;
     if (const char* ev = getenv("HPV_BWD_STAGGER_NS")) ctx->bwd_stagger_ns = atoi(ev);
     if (const char* ev = getenv("HPV_PEER_TIMEOUT_S")) { const double v = atof(ev); if (v > 0) ctx->peer_timeout_ns = (unsigned long long)(v * 1e9); }
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
@@ -1317,7 +1329,8 @@ int hpv_kernel_info(hpv_ctx* c, int* info, int n) {
     { int r = ensure_ready(c); if (r) return r; }
     const int v[15] = {c->n_sm, c->part.n_ctas, HPV_THREADS, (int)c->fwd_smem, c->fwd_ctas_per_sm,
                        c->bwd_grid, c->bwd_block, (int)c->bwd_smem, c->bwd_ctas_per_sm,
-                       c->adj_grid, (int)c->adj_smem, c->net.hp, bwd_key_of(c).dir, c->fwd_tc_active ? 1 : 0, c->bwd_tc_active ? 1 : 0};
+                       c->adj_grid, (int)c->adj_smem, c->net.hp, bwd_key_of(c).dir, c->fwd_tc_active ? 1 : 0,
+                       c->bwd_tc_active ? (c->bwd_tcw_active ? 2 : 1) : 0};
     for (int i = 0; i < n && i < 15; ++i) info[i] = v[i];
     return HPV_OK;
 }

@@ -37,12 +37,23 @@ hpv_mlpbwd_tc_kernel(const __grid_constant__ HpvBwdArgs a) {
     if constexpr (hpv_tc_supported(HpvMode<DIM, MX, MY>::NCH, HP)) hpv_mlpbwd_tc_body<DIM, MX, MY, HP, ACT>(c, a);
 }
 
+// ... and with the weight gradients on the tensor cores as well (hpv_varbwd_tcw.cuh).
+template <int DIM, int MX, int MY, int HP, int ACT>
+__global__ void __launch_bounds__(HPV_THREADS, (hpv_tcw_tmem_need(HpvMode<DIM, MX, MY>::NCH, HP, 3) <= 256 ? 2 : 1))
+hpv_mlpbwd_tcw_kernel(const __grid_constant__ HpvBwdArgs a) {
+    extern __shared__ __align__(128) unsigned char hpv_smem_tcw[];
+    HpvCta c;
+    c.tid = threadIdx.x; c.nthreads = blockDim.x; c.bid = blockIdx.x; c.nblocks = gridDim.x;
+    c.smem = hpv_smem_tcw; c.emu = nullptr;
+    if constexpr (HP <= 24) hpv_mlpbwd_tcw_body<DIM, MX, MY, HP, ACT>(c, a);
+}
+
 // Resident CTAs per SM of a tensor-core kernel from its resources.  (cudaOccupancyMaxActiveBlocksPerMultiprocessor
 // answered 1 for the 89 KB / 128-register headline instance of the forward kernel although the hardware co-schedules
 // two -- ncu: block limit registers 2, shared memory 2 -- so the bound is computed here; nothing depends on
 // co-residency for correctness, the figure only sizes the persistent grid.)
 template <typename K>
-static cudaError_t hpv_tc_resident(K k, int block, size_t smem, int nch, int hp, long long* out) {
+static cudaError_t hpv_tc_resident(K k, int block, size_t smem, int tmem_cols, long long* out) {
     int n = 0;
     cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, block, smem);
     if (err != cudaSuccess) return err;
@@ -57,7 +68,7 @@ static cudaError_t hpv_tc_resident(K k, int block, size_t smem, int nch, int hp,
     const int by_smem = (int)((size_t)smem_sm / (smem + fa.sharedSizeBytes + 1024));
     const int own = by_regs < by_smem ? by_regs : by_smem;
     if (n < own) n = own;
-    const int by_tmem = 512 / hpv_tc_tmem_cols(nch, hp);
+    const int by_tmem = 512 / tmem_cols;
     *out = n < by_tmem ? n : by_tmem;
     return cudaSuccess;
 }
@@ -136,23 +147,37 @@ static cudaError_t hpv_do(const HpvLaunch& l) {
             auto k = hpv_varfwd_tc_kernel<DIM, MX, MY, HP, ACT>;
             if ((err = hpv_prepare(k, l.smem, prepared)) != cudaSuccess) return err;
             if (l.op == 1) {
-                return hpv_tc_resident(k, l.block, l.smem, HpvMode<DIM, MX, MY>::NCH, HP, l.out);
+                return hpv_tc_resident(k, l.block, l.smem, hpv_tc_tmem_cols(HpvMode<DIM, MX, MY>::NCH, HP), l.out);
             }
             k<<<l.grid, l.block, l.smem, l.stream>>>(*l.var);
         }
     } else if constexpr (KIND == HPV_K_MLPBWD_TC) {
-        if constexpr (!hpv_tc_supported(HpvMode<DIM, MX, MY>::NCH, HP)) {
+        typedef HpvMode<DIM, MX, MY> M;
+        if constexpr (!hpv_tc_supported(M::NCH, HP)) {
             return cudaErrorInvalidValue;
         } else {
+            const int nhid = l.bwd->v.nhid;
+            bool wg = false;
+            if constexpr (HP <= 24) wg = l.wg != 0 && hpv_tcw_supported(M::NCH, HP, nhid);
+            if (l.op == 5) { *l.out = wg ? 1 : 0; return cudaSuccess; }       // which variant would run
+            if constexpr (HP <= 24) {
+                if (wg) {
+                    auto k = hpv_mlpbwd_tcw_kernel<DIM, MX, MY, HP, ACT>;
+                    if (l.op == 2) { *l.out = (long long)hpv_bwd_tcw_smem(DIM, HP, M::NCH, nhid).total * 4; return cudaSuccess; }
+                    static size_t prepared_w[16] = {0};
+                    if ((err = hpv_prepare(k, l.smem, prepared_w)) != cudaSuccess) return err;
+                    if (l.op == 1) return hpv_tc_resident(k, l.block, l.smem, hpv_tcw_tmem_need(M::NCH, HP, nhid) <= 256 ? 256 : 512, l.out);
+                    return hpv_launch_pdl(k, l.grid, l.block, l.smem, l.stream, *l.bwd);
+                }
+            }
             auto k = hpv_mlpbwd_tc_kernel<DIM, MX, MY, HP, ACT>;
             if (l.op == 2) {
-                typedef HpvMode<DIM, MX, MY> M;
-                const HpvBwdTcSmem L = hpv_bwd_tc_smem(DIM, HP, M::NCH, 1 + (M::DX ? 1 : 0) + (M::DY ? 1 : 0), l.bwd->v.nhid);
+                const HpvBwdTcSmem L = hpv_bwd_tc_smem(DIM, HP, M::NCH, 1 + (M::DX ? 1 : 0) + (M::DY ? 1 : 0), nhid);
                 *l.out = (long long)L.total * 4;
                 return cudaSuccess;
             }
             if ((err = hpv_prepare(k, l.smem, prepared)) != cudaSuccess) return err;
-            if (l.op == 1) return hpv_tc_resident(k, l.block, l.smem, HpvMode<DIM, MX, MY>::NCH, HP, l.out);
+            if (l.op == 1) return hpv_tc_resident(k, l.block, l.smem, hpv_tc_tmem_cols(M::NCH, HP), l.out);
             return hpv_launch_pdl(k, l.grid, l.block, l.smem, l.stream, *l.bwd);
         }
     } else if constexpr (KIND == HPV_K_MLPBWD) {

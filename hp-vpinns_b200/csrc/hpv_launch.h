@@ -7,6 +7,7 @@
 #include "hpv_points.cuh"
 #include "hpv_varfwd_tc.cuh"
 #include "hpv_varbwd_tc.cuh"
+#include "hpv_varbwd_tcw.cuh"
 
 // dir != 0 (reverse sweep only): the directional mode HpvMode<2, 1, 0> instead of <2, 1, 1>.
 // Launch with programmatic stream serialisation: the kernel's CTAs may start before the previous kernel of the
@@ -31,7 +32,7 @@ inline cudaError_t hpv_launch_pdl(void (*kernel)(KArgs...), int grid, int block,
 }
 #endif
 
-struct HpvKernelKey { int dim, mx, my, hp, act, dir; };
+struct HpvKernelKey { int dim, mx, my, hp, act, dir, wg; };   // wg: tensor-core reverse sweep with the weight gradients on the tensor cores too
 
 enum { HPV_K_VARFWD = 0, HPV_K_MLPBWD = 1, HPV_K_POINTS = 2, HPV_K_VARFWD_TC = 3, HPV_K_MLPBWD_TC = 4 };
 
@@ -49,6 +50,7 @@ struct HpvLaunch {
     const HpvPointArgs* pts;
     float* gbar_out;
     long long* out;
+    int wg;                    // reverse sweep, tensor-core form: weight gradients on the tensor cores too (when supported)
 };
 
 #define HPV_DECL(hp) \

@@ -54,3 +54,19 @@ def test_forward_kernel_keeps_the_uniform_datapath():
     uniform, vector, ur_ffma2 = _weight_loads(s)
     assert uniform >= 40 and ur_ffma2 >= 100, (uniform, vector, ur_ffma2)
     assert vector <= 30
+
+
+def test_tensor_core_kernels_use_tcgen05_tmem_and_the_bulk_copy_engine():
+    """BASELINE.json north_star: MLP layer products on tensor-core tiles, tables staged through TMA.  The headline
+    instances of the tensor-core forward kernel and reverse sweep must contain the Blackwell instructions
+    (tcgen05.mma -> UTC*MMA, tcgen05.ld/st -> LDTM/STTM, cp.async.bulk -> UBLKCP) and issue their MMAs densely
+    (operands in uniform registers: few R2UR transfers per MMA)."""
+    fwd = _sass("hpv_k_h20_fwdtc.o", "_Z20hpv_varfwd_tc_kernelILi2ELi1ELi1ELi20ELi1EEv10HpvVarArgs")
+    n_mma = len(re.findall(r"UTC\w*MMA", fwd))
+    assert n_mma >= 54, n_mma                           # 3 channels x 9 MMAs, for the two TMEM base addresses
+    assert "LDTM" in fwd and "STTM" in fwd and "UBLKCP" in fwd
+    assert fwd.count("R2UR") <= 4 * n_mma
+    bwd = _sass("hpv_k_h20_bwdtc.o", "_Z21hpv_mlpbwd_tcw_kernelILi2ELi1ELi0ELi20ELi1EEv10HpvBwdArgs")
+    n_mma_b = len(re.findall(r"UTC\w*MMA", bwd))
+    assert n_mma_b >= 2 * (18 + 32), n_mma_b            # products (2 channels x 9) + weight gradients (16 K steps x 2), two bases
+    assert "LDTM" in bwd and "STTM" in bwd
