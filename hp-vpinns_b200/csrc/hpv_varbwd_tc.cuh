@@ -45,20 +45,45 @@ HPV_HD HpvBwdTcSmem hpv_bwd_tc_smem(int dim, int hp, int nch, int nch1, int nhid
 #if defined(__CUDACC__)
 
 // This thread's units of one channel block [ch][128 rows][SP] <-> registers (64-bit accesses of the packed pairs).
+// 128-bit accesses wherever the 16-byte alignment allows (rows are SP floats apart, SP chosen so that the 128-bit
+// accesses of a quarter warp fall into distinct banks; plain 64-bit accesses of the pairs measured 4-way conflicts):
+// HPH = 10: units 0-9 = quad, quad, pair; units 10-19 = pair, quad, quad.
 template <class M, int HPH, int SP, class S>
 __device__ __forceinline__ void hpv_tc_store_half(float* slot, int prow, int u0, const S& s) {
+    constexpr int NPRS = HPH / 2;
     hpv_each_ch<M>(s, [&](const hpv_pair* a, int ch) {
-        hpv_pair* row = reinterpret_cast<hpv_pair*>(slot + ((size_t)ch * HPV_TC_MTILE + prow) * SP + u0);
+        float* row = slot + ((size_t)ch * HPV_TC_MTILE + prow) * SP + u0;
+        if constexpr (NPRS % 2 == 0) {
 #pragma unroll
-        for (int m = 0; m < HPH / 2; ++m) row[m] = a[m];
+            for (int m = 0; m < NPRS; m += 2) hpv_st_pairs(row + 2 * m, a[m], a[m + 1]);
+        } else if ((u0 & 3) == 0) {                         // quads first, one trailing pair
+#pragma unroll
+            for (int m = 0; m + 1 < NPRS; m += 2) hpv_st_pairs(row + 2 * m, a[m], a[m + 1]);
+            *reinterpret_cast<hpv_pair*>(row + 2 * (NPRS - 1)) = a[NPRS - 1];
+        } else {                                            // one leading pair, then quads
+            *reinterpret_cast<hpv_pair*>(row) = a[0];
+#pragma unroll
+            for (int m = 1; m + 1 < NPRS; m += 2) hpv_st_pairs(row + 2 * m, a[m], a[m + 1]);
+        }
     });
 }
 template <class M, int HPH, int SP, class S>
 __device__ __forceinline__ void hpv_tc_load_half(const float* slot, int prow, int u0, S& s) {
+    constexpr int NPRS = HPH / 2;
     hpv_each_ch<M>(s, [&](hpv_pair* a, int ch) {
-        const hpv_pair* row = reinterpret_cast<const hpv_pair*>(slot + ((size_t)ch * HPV_TC_MTILE + prow) * SP + u0);
+        const float* row = slot + ((size_t)ch * HPV_TC_MTILE + prow) * SP + u0;
+        if constexpr (NPRS % 2 == 0) {
 #pragma unroll
-        for (int m = 0; m < HPH / 2; ++m) a[m] = row[m];
+            for (int m = 0; m < NPRS; m += 2) hpv_ld_pairs(row + 2 * m, a[m], a[m + 1]);
+        } else if ((u0 & 3) == 0) {
+#pragma unroll
+            for (int m = 0; m + 1 < NPRS; m += 2) hpv_ld_pairs(row + 2 * m, a[m], a[m + 1]);
+            a[NPRS - 1] = *reinterpret_cast<const hpv_pair*>(row + 2 * (NPRS - 1));
+        } else {
+            a[0] = *reinterpret_cast<const hpv_pair*>(row);
+#pragma unroll
+            for (int m = 1; m + 1 < NPRS; m += 2) hpv_ld_pairs(row + 2 * m, a[m], a[m + 1]);
+        }
     });
 }
 // Split this thread's units of every channel and store them as the A operand (hi, lo) of the next product.
@@ -66,16 +91,7 @@ template <class M, int HPH, int KP, class S>
 __device__ __forceinline__ void hpv_tc_store_A(uint32_t tb_lane, int u0, const S& s) {
     constexpr uint32_t colAhi = M::NCH * HPV_TC_NPAD, colAlo = colAhi + M::NCH * KP;
     hpv_each_ch<M>(s, [&](const hpv_pair* a, int ch) {
-        uint32_t hi[HPH], lo[HPH];
-#pragma unroll
-        for (int m = 0; m < HPH / 2; ++m) {
-            float h0, h1;
-            hpv_unpack(a[m], h0, h1);
-            hpv_split_trunc(h0, hi[2 * m], lo[2 * m]);
-            hpv_split_trunc(h1, hi[2 * m + 1], lo[2 * m + 1]);
-        }
-        hpv_tmem_st_n<HPH>(tb_lane + colAhi + ch * KP + u0, hi);
-        hpv_tmem_st_n<HPH>(tb_lane + colAlo + ch * KP + u0, lo);
+        hpv_tc_split_store<HPH>(tb_lane + colAhi + ch * KP + u0, tb_lane + colAlo + ch * KP + u0, a);
     });
 }
 // The accumulators of a product, channel by channel as they complete -> this thread's units.
@@ -206,14 +222,15 @@ __device__ __forceinline__ void hpv_mlpbwd_tc_body(const HpvCta& c, const HpvBwd
         }
     };
 
-#pragma unroll 1
-    for (int tile = t_begin; tile < t_end; ++tile) {
+    // coordinates and field adjoints of this thread's point of a tile; fetched one tile ahead (the loads would
+    // otherwise sit exposed at the top of every tile: all warps of the CTA start a tile in lockstep)
+    auto load_inputs = [&](int tile, float& x, float& y, float (&gb)[HPV_MAX_TERMS]) {
         const long long gpl = (long long)tile * HPV_TC_MTILE + prow;
-        const bool valid = gpl < (long long)ba.n_points;
-        const int gp = valid ? (int)gpl : 0;
-        float x = 0.0f, y = 0.0f;
-        float gbar[HPV_MAX_TERMS] = {0.0f, 0.0f};
-        if (valid) {
+        x = 0.0f; y = 0.0f;
+#pragma unroll
+        for (int t = 0; t < HPV_MAX_TERMS; ++t) gb[t] = 0.0f;
+        if (tile < t_end && gpl < (long long)ba.n_points) {
+            const int gp = (int)gpl;
             if (ba.pts) {
                 x = ba.pts[(size_t)gp * DIM];
                 if (DIM == 2) y = ba.pts[(size_t)gp * DIM + 1];
@@ -225,8 +242,19 @@ __device__ __forceinline__ void hpv_mlpbwd_tc_body(const HpvCta& c, const HpvBwd
             }
 #pragma unroll
             for (int t = 0; t < HPV_MAX_TERMS; ++t)
-                if (t < a.n_terms) gbar[t] = ba.Gbar[(size_t)t * ba.n_points + gp];
+                if (t < a.n_terms) gb[t] = ba.Gbar[(size_t)t * ba.n_points + gp];
         }
+    };
+    float nx, ny, ngbar[HPV_MAX_TERMS];
+    load_inputs(t_begin, nx, ny, ngbar);
+
+#pragma unroll 1
+    for (int tile = t_begin; tile < t_end; ++tile) {
+        const float x = nx, y = ny;
+        float gbar[HPV_MAX_TERMS];
+#pragma unroll
+        for (int t = 0; t < HPV_MAX_TERMS; ++t) gbar[t] = ngbar[t];
+        load_inputs(tile + 1, nx, ny, ngbar);
         float gf[HPV_NFIELDS];
 #pragma unroll
         for (int k = 0; k < HPV_NFIELDS; ++k) gf[k] = 0.0f;

@@ -121,6 +121,23 @@ __device__ __forceinline__ void hpv_split_trunc(float x, uint32_t& hi, uint32_t&
     lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
+// One channel's units of this thread (packed pairs) -> A operand: hi = TF32 part, lo = x - hi, stored with the widest
+// tcgen05.st shapes.  (Storing pair by pair with .x2 straight from the pairs, to save the register moves that assemble
+// the aligned groups of 8, measured 4 % SLOWER on the forward kernel: 67.0 vs 64.5 us at C3, profiles/r2_tuning.)
+template <int HPH>
+__device__ __forceinline__ void hpv_tc_split_store(uint32_t addr_hi, uint32_t addr_lo, const hpv_pair* a) {
+    uint32_t hi[HPH], lo[HPH];
+#pragma unroll
+    for (int m = 0; m < HPH / 2; ++m) {
+        float h0, h1;
+        hpv_unpack(a[m], h0, h1);
+        hpv_split_trunc(h0, hi[2 * m], lo[2 * m]);
+        hpv_split_trunc(h1, hi[2 * m + 1], lo[2 * m + 1]);
+    }
+    hpv_tmem_st_n<HPH>(addr_hi, hi);
+    hpv_tmem_st_n<HPH>(addr_lo, lo);
+}
+
 // The MMAs of one hidden-layer product for all channels, issued by one thread.  TB (TMEM base of this CTA), the
 // column offsets and the descriptor strides are compile-time constants and the shared-memory addresses are uniform,
 // so every operand sits in a uniform register without a transfer from the vector registers: the instructions go out
@@ -316,16 +333,7 @@ __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVar
                 if (l == nhid) break;
                 // split and store as the A operand of the next product
                 hpv_each_ch<M>(s, [&](hpv_pair* hp_, int ch) {
-                    uint32_t hi[HPH], lo[HPH];
-#pragma unroll
-                    for (int m = 0; m < NPR; ++m) {
-                        float h0, h1;
-                        hpv_unpack(hp_[m], h0, h1);
-                        hpv_split_trunc(h0, hi[2 * m], lo[2 * m]);
-                        hpv_split_trunc(h1, hi[2 * m + 1], lo[2 * m + 1]);
-                    }
-                    hpv_tmem_st_n<HPH>(tb + lane_base + colAhi + ch * KP + u0, hi);
-                    hpv_tmem_st_n<HPH>(tb + lane_base + colAlo + ch * KP + u0, lo);
+                    hpv_tc_split_store<HPH>(tb + lane_base + colAhi + ch * KP + u0, tb + lane_base + colAlo + ch * KP + u0, hp_);
                 });
                 hpv_tmem_wait_st();
                 hpv_tc_fence_before();
