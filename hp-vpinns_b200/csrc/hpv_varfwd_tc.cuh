@@ -162,10 +162,62 @@ __device__ __forceinline__ void hpv_tc_issue_layer(uint32_t bhi, uint32_t blo, u
     }
 }
 
+
+// Scalar form of a layer state for the tensor-core kernels: the values travel between TMEM and the arithmetic as
+// plain 32-bit registers (tcgen05.ld/st operate on 32-bit registers; the packed FP32x2 form of hpv_math.cuh costs a
+// register move per value to build and take apart the pairs around every TMEM access -- 170 of the 830 instructions
+// per thread and tile of the first version, profiles/r2_tuning/varfwd_tc_segments.txt).
+template <int DIM, int MX, int MY, int N>
+struct HpvStateS {
+    typedef HpvMode<DIM, MX, MY> M;
+    float v[N];
+    float dx[M::DX ? N : 1];
+    float dy[M::DY ? N : 1];
+    float ex[M::EX ? N : 1];
+    float ey[M::EY ? N : 1];
+};
+template <class M, class S, class F>
+__device__ __forceinline__ void hpv_each_ch_s(S& s, F f) {
+    f(s.v, M::C_V);
+    if constexpr (M::DX) f(s.dx, M::C_DX);
+    if constexpr (M::DY) f(s.dy, M::C_DY);
+    if constexpr (M::EX) f(s.ex, M::C_EX);
+    if constexpr (M::EY) f(s.ey, M::C_EY);
+}
+//   h = s(z);  dh = s'(z) dz;  d2h = s''(z) dz^2 + s'(z) d2z     (in place)
+template <int DIM, int MX, int MY, int N, int ACT>
+__device__ __forceinline__ void hpv_activate_s(HpvStateS<DIM, MX, MY, N>& s) {
+    typedef HpvMode<DIM, MX, MY> M;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        float a, s1, s2;
+        hpv_act<ACT>(s.v[j], a, s1, s2);
+        s.v[j] = a;
+        if constexpr (M::DX) {
+            const float dz = s.dx[j];
+            if constexpr (M::EX) s.ex[j] = fmaf(s2 * dz, dz, s1 * s.ex[j]);
+            s.dx[j] = s1 * dz;
+        }
+        if constexpr (M::DY) {
+            const float dz = s.dy[j];
+            if constexpr (M::EY) s.ey[j] = fmaf(s2 * dz, dz, s1 * s.ey[j]);
+            s.dy[j] = s1 * dz;
+        }
+    }
+}
+template <int N>
+__device__ __forceinline__ void hpv_tc_split_store_s(uint32_t addr_hi, uint32_t addr_lo, const float* h) {
+    uint32_t hi[N], lo[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) hpv_split_trunc(h[j], hi[j], lo[j]);
+    hpv_tmem_st_n<N>(addr_hi, hi);
+    hpv_tmem_st_n<N>(addr_lo, lo);
+}
+
 template <int DIM, int MX, int MY, int HP, int ACT>
 __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVarArgs& a) {
     typedef HpvMode<DIM, MX, MY> M;
-    constexpr int NCH = M::NCH, KP = HpvTcDims<HP>::KP, HPH = HpvTcDims<HP>::HPH, NPR = HPH / 2;
+    constexpr int NCH = M::NCH, KP = HpvTcDims<HP>::KP, HPH = HpvTcDims<HP>::HPH;
     constexpr uint32_t TCOLS = (NCH * HPV_TC_NPAD + 2 * NCH * KP) <= 256 ? 256u : 512u;
     static_assert(HPH % 2 == 0, "HP/2 must be even (packed pairs)");
     const int T = c.nthreads, tid = c.tid;
@@ -294,46 +346,38 @@ __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVar
             const int j = pc / Q, i = pc - j * Q;
             const float x = fmaf(hwx, s_xi1[i], lox);
             const float y = (DIM == 2) ? fmaf(hwy, s_xi1[j], loy) : 0.0f;
-            HpvState<DIM, MX, MY, HPH> s;
+            HpvStateS<DIM, MX, MY, HPH> s;
             // first layer, this thread's units: z = b1 + x W1[0,:] (+ y W1[1,:]); dz/dx = W1[0,:]; d2z = 0
-            {
-                const hpv_pair xx = hpv_dup(x), yy = hpv_dup(y);
 #pragma unroll
-                for (int m = 0; m < NPR; ++m) {
-                    const int u = u0 + 2 * m;
-                    const hpv_pair wx = hpv_pack(W1[u], W1[u + 1]);
-                    hpv_pair zz = hpv_fma2r(xx, wx, hpv_pack(b1[u], b1[u + 1]));
-                    if constexpr (DIM == 2) {
-                        const hpv_pair wy = hpv_pack(W1[HP + u], W1[HP + u + 1]);
-                        zz = hpv_fma2r(yy, wy, zz);
-                        if constexpr (M::DY) s.dy.p[m] = wy;
-                    }
-                    s.v.p[m] = zz;
-                    if constexpr (M::DX) s.dx.p[m] = wx;
-                    if constexpr (M::EX) s.ex.p[m] = hpv_dup(0.0f);
-                    if constexpr (M::EY) s.ey.p[m] = hpv_dup(0.0f);
+            for (int jj = 0; jj < HPH; ++jj) {
+                const int u = u0 + jj;
+                float zz = fmaf(x, W1[u], b1[u]);
+                if constexpr (DIM == 2) {
+                    zz = fmaf(y, W1[HP + u], zz);
+                    if constexpr (M::DY) s.dy[jj] = W1[HP + u];
                 }
+                s.v[jj] = zz;
+                if constexpr (M::DX) s.dx[jj] = W1[u];
+                if constexpr (M::EX) s.ex[jj] = 0.0f;
+                if constexpr (M::EY) s.ey[jj] = 0.0f;
             }
 #pragma unroll 1
             for (int l = 1; l <= nhid; ++l) {
                 if (l > 1) {
                     // pre-activations of hidden layer l from TMEM, channel by channel as the products complete
-                    hpv_each_ch<M>(s, [&](hpv_pair* zp, int ch) {
+                    hpv_each_ch_s<M>(s, [&](float* zp, int ch) {
                         hpv_mbar_wait(&s_bar[ch], phase);
                         hpv_tc_fence_after();
-                        float v[HPH];
-                        hpv_tmem_ld_n<HPH>(tb + lane_base + colD + ch * HPV_TC_NPAD + u0, v);
+                        hpv_tmem_ld_n<HPH>(tb + lane_base + colD + ch * HPV_TC_NPAD + u0, zp);
                         hpv_tmem_wait_ld();
-#pragma unroll
-                        for (int m = 0; m < NPR; ++m) zp[m] = hpv_pack(v[2 * m], v[2 * m + 1]);
                     });
                     phase ^= 1;
                 }
-                hpv_activate<DIM, MX, MY, HPH, ACT>(s);                  // post-activations h, dh, d2h of layer l
+                hpv_activate_s<DIM, MX, MY, HPH, ACT>(s);                // post-activations h, dh, d2h of layer l
                 if (l == nhid) break;
                 // split and store as the A operand of the next product
-                hpv_each_ch<M>(s, [&](hpv_pair* hp_, int ch) {
-                    hpv_tc_split_store<HPH>(tb + lane_base + colAhi + ch * KP + u0, tb + lane_base + colAlo + ch * KP + u0, hp_);
+                hpv_each_ch_s<M>(s, [&](float* hp_, int ch) {
+                    hpv_tc_split_store_s<HPH>(tb + lane_base + colAhi + ch * KP + u0, tb + lane_base + colAlo + ch * KP + u0, hp_);
                 });
                 hpv_tmem_wait_st();
                 hpv_tc_fence_before();
@@ -352,15 +396,10 @@ __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVar
             // output layer: partial sums over this thread's units, combined across the two halves
             {
                 float acc[NCH];
-                hpv_each_ch<M>(s, [&](hpv_pair* hp_, int ch) {
+                hpv_each_ch_s<M>(s, [&](float* hp_, int ch) {
                     float sacc = 0.0f;
 #pragma unroll
-                    for (int m = 0; m < NPR; ++m) {
-                        float h0, h1;
-                        hpv_unpack(hp_[m], h0, h1);
-                        sacc = fmaf(h0, Wo[u0 + 2 * m], sacc);
-                        sacc = fmaf(h1, Wo[u0 + 2 * m + 1], sacc);
-                    }
+                    for (int jj = 0; jj < HPH; ++jj) sacc = fmaf(hp_[jj], Wo[u0 + jj], sacc);
                     acc[ch] = sacc;
                 });
                 if (half == 1) {
