@@ -123,7 +123,7 @@ __device__ __forceinline__ void hpv_split_trunc(float x, uint32_t& hi, uint32_t&
 
 // One channel's units of this thread (packed pairs) -> A operand: hi = TF32 part, lo = x - hi, stored with the widest
 // tcgen05.st shapes.  (Storing pair by pair with .x2 straight from the pairs, to save the register moves that assemble
-// the aligned groups of 8, measured 4 % SLOWER on the forward kernel: 67.0 vs 64.5 us at C3, profiles/r2_tuning.)
+// the aligned groups of 8, measured 4 % SLOWER on the forward kernel: 67.0 vs 64.5 us at C3, profiles/round2_tuning.)
 template <int HPH>
 __device__ __forceinline__ void hpv_tc_split_store(uint32_t addr_hi, uint32_t addr_lo, const hpv_pair* a) {
     uint32_t hi[HPH], lo[HPH];
@@ -166,7 +166,7 @@ __device__ __forceinline__ void hpv_tc_issue_layer(uint32_t bhi, uint32_t blo, u
 // Scalar form of a layer state for the tensor-core kernels: the values travel between TMEM and the arithmetic as
 // plain 32-bit registers (tcgen05.ld/st operate on 32-bit registers; the packed FP32x2 form of hpv_math.cuh costs a
 // register move per value to build and take apart the pairs around every TMEM access -- 170 of the 830 instructions
-// per thread and tile of the first version, profiles/r2_tuning/varfwd_tc_segments.txt).
+// per thread and tile of the first version, profiles/round2_tuning/varfwd_tc_segments.txt).
 template <int DIM, int MX, int MY, int N>
 struct HpvStateS {
     typedef HpvMode<DIM, MX, MY> M;
