@@ -12,6 +12,7 @@
 #include "../../hp-vpinns_b200/csrc/hpv_host_prep.h"
 #include "../../hp-vpinns_b200/csrc/hpv_varbwd.cuh"
 #include "../../hp-vpinns_b200/csrc/hpv_points.cuh"
+#include "../../hp-vpinns_b200/csrc/hpv_varbwd_tcw.cuh"     // host-side plans of the tensor-core kernels (device code is compiled out)
 
 struct HpvEmu {
     std::barrier<>* bar;                 // the CTA barrier (__syncthreads)
@@ -149,6 +150,25 @@ int hpv_emu_gw_n(int dim, int hp, int nhid) { return hpv_gw_n(dim, hp, nhid); }
 int hpv_emu_theta_pad_n(int dim, int hp, int nhid) { return hpv_theta_pad_n(dim, hp, nhid); }
 int hpv_emu_off_wt(int dim, int hp, int l) { return hpv_off_wt(dim, hp, l); }
 int hpv_emu_off_wl(int dim, int hp, int l) { return hpv_off_wl(dim, hp, l); }
+
+// Plans of the tensor-core kernels: TMEM columns and shared-memory layouts (offsets in floats).
+// out[0..7] forward: total, B, bar, th, part, tab0, P, G;  out[8..13] reverse sweep (FFMA weight gradients): total, B, bar,
+// slots, gw, slot_sz;  out[14..18] reverse sweep (tensor-core weight gradients): total, B, bar, op, slots
+int hpv_emu_tc_plan(int dim, int hp, int nch, int nch1, int nhid, int Q, int rows, int n_terms, int ltab, int rtab, int* out) {
+    HpvVarArgs a;
+    memset(&a, 0, sizeof(a));
+    a.Q = Q; a.rows = rows; a.n_terms = n_terms; a.nhid = nhid;
+    for (int t = 0; t < n_terms; ++t) { a.terms[t].ltab = t == 0 ? ltab : rtab; a.terms[t].rtab = t == 0 ? rtab : ltab; }
+    const HpvFwdTcSmem f = hpv_fwd_tc_smem(a, dim, hp, nch);
+    out[0] = f.total; out[1] = f.B; out[2] = f.bar; out[3] = f.th; out[4] = f.part; out[5] = f.tab[ltab]; out[6] = f.P; out[7] = f.G;
+    const HpvBwdTcSmem b = hpv_bwd_tc_smem(dim, hp, nch, nch1, nhid);
+    out[8] = b.total; out[9] = b.B; out[10] = b.bar; out[11] = b.slots; out[12] = b.gw; out[13] = b.slot_sz;
+    const HpvBwdTcwSmem w = hpv_bwd_tcw_smem(dim, hp, nch, nhid);
+    out[14] = w.total; out[15] = w.B; out[16] = w.bar; out[17] = w.op; out[18] = w.slots;
+    return hpv_tc_tmem_need(nch, hp);
+}
+int hpv_emu_tcw_tmem_need(int nch, int hp, int nhid) { return hpv_tcw_tmem_need(nch, hp, nhid); }
+int hpv_emu_tcw_supported(int nch, int hp, int nhid) { return hpv_tcw_supported(nch, hp, nhid) ? 1 : 0; }
 
 // Variational loss forward (+ backward when grad_theta != NULL) on emulated CTAs.
 //   n_ctas_fwd / n_ctas_bwd / bwd_block choose the launch geometry (to exercise the split-element paths).

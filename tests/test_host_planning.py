@@ -67,3 +67,44 @@ def test_compact_gradient_layout_is_a_bijection_onto_the_primary_parameters(dim,
     # hidden matrix l sits at the same relative position in both layouts
     for l in range(1, nhid):
         assert L.hpv_emu_gw_of_padded(dim, hp, nhid, L.hpv_emu_off_wl(dim, hp, l)) == (dim + 1) * hp + (l - 1) * (hp * hp + hp)
+
+
+def _tc_plan(dim, hp, nch, nch1, nhid, Q, rows, n_terms, ltab=0, rtab=1):
+    L = E.lib()
+    out = np.zeros(19, dtype=np.int32)
+    need = L.hpv_emu_tc_plan(dim, hp, nch, nch1, nhid, Q, rows, n_terms, ltab, rtab, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    return need, out
+
+
+def test_tensor_core_plans_of_the_headline_configuration():
+    """C3/C4: [2,20,20,20,1], value + two tangents forward, directional reverse sweep.  The tensor-core kernels need two
+    CTAs per SM: <= 256 TMEM columns and <= 113 KB of shared memory each; the weight tiles and mbarriers must sit
+    at the alignments the hardware asks for."""
+    need, o = _tc_plan(2, 20, 3, 3, 3, 80, 80, 2)
+    assert need == 3 * 32 + 2 * 3 * 24 == 240                     # D + A_hi + A_lo
+    assert o[0] * 4 <= 113 * 1024                                 # forward: two CTAs per SM
+    assert o[1] % 32 == 0 and o[2] % 2 == 0                       # B tiles 128-byte aligned, mbarriers 8-byte aligned
+    assert o[5] % 4 == 0                                          # tables: 16-byte aligned destination of the bulk copy
+    assert o[1] + 2 * 2 * 24 * 32 <= o[2]                         # two layers of (hi, lo) weight tiles before the barriers
+    need_b, ob = _tc_plan(2, 20, 2, 2, 3, 80, 80, 2)              # directional reverse sweep: 2 channels
+    assert need_b == 160
+    assert ob[8] * 4 <= 113 * 1024 and ob[9] % 32 == 0 and ob[10] % 2 == 0
+    assert ob[14] * 4 <= 113 * 1024 and ob[15] % 32 == 0 and ob[16] % 2 == 0
+    L = E.lib()
+    assert L.hpv_emu_tcw_tmem_need(2, 20, 3) == 160 + 2 * 32 <= 256
+    assert L.hpv_emu_tcw_supported(2, 20, 3) == 1 and L.hpv_emu_tcw_supported(2, 32, 3) == 0 and L.hpv_emu_tcw_supported(2, 20, 1) == 0
+
+
+@settings(max_examples=100, deadline=None)
+@given(hp=st.sampled_from([8, 20, 32]), nch=st.integers(1, 5), nhid=st.integers(1, 8), Q=st.integers(2, 128), n_terms=st.integers(1, 2),
+       dim=st.sampled_from([1, 2]))
+def test_tensor_core_plan_invariants(hp, nch, nhid, Q, n_terms, dim):
+    rows = Q if dim == 2 else 1
+    need, o = _tc_plan(dim, hp, nch, min(nch, 3), nhid, Q, rows, n_terms)
+    kp = ((hp + 1 + 7) // 8) * 8
+    assert need == nch * 32 + 2 * nch * kp
+    for base in (0, 8, 14):                                       # the three kernels' plans
+        total, B, bar = o[base], o[base + 1], o[base + 2]
+        assert 0 < B <= bar < total and B % 32 == 0 and bar % 2 == 0
+    # regions of the forward plan do not overlap: G < tables < P < th < part < B
+    assert o[7] < o[5] < o[6] <= o[3] < o[4] < o[1]
