@@ -133,6 +133,9 @@ HPV_HD void hpv_matmul_slot(const float* W, const float* b, const float* slot, i
     HpvF4 xn[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) xn[c] = hpv_ld4(row + (size_t)c * T * SP);
+#if defined(HPV_EXP_NO_PROD)      // timing experiment only (tools/gpu_r2k.sh): what the kernel costs without the products
+    if (tid >= 0) return;
+#endif
 #pragma unroll 1
     for (int i4 = 0; i4 < HP / 4; ++i4, wr0 += 4 * HP) {
         float x[NCH][4];

@@ -206,6 +206,9 @@ struct HpvBwdSmem {
 // warps), CHS rows between the channel blocks of IN / ADJ.
 template <int SPI, int SPA, int NCH, int NROWS, int NJ, int TN, bool BIAS, int KIND, int HP, int DIM, int NPTS = 32, int CHS = 32>
 HPV_HD void hpv_wgrad_warp(const HpvCta& c, const float* IN, const float* ADJ, float* D, float* Db, const float* cst) {
+#if defined(HPV_EXP_NO_WGRAD)     // timing experiment only (tools/gpu_r2k.sh): what the kernel costs without the weight gradients
+    if (c.tid >= 0) return;
+#endif
     constexpr int NI = (NROWS + (BIAS ? 1 : 0) + 3) / 4;
     constexpr int NTILES = NI * NJ;
     constexpr int KSW = NTILES > 16 ? 1 : (NTILES > 8 ? 2 : (NTILES > 4 ? 4 : (NTILES > 2 ? 8 : 16)));

@@ -98,7 +98,9 @@ __device__ __forceinline__ void hpv_tc_store_A(uint32_t tb_lane, int u0, const S
 template <class M, int HPH, class S>
 __device__ __forceinline__ void hpv_tc_load_D(uint32_t tb_lane, int u0, uint64_t* bar, uint32_t phase, S& s) {
     hpv_each_ch<M>(s, [&](hpv_pair* zp, int ch) {
+#if !defined(HPV_EXP_NO_MMA)      // timing experiment only (tools/gpu_r2k.sh): no products issued, nothing to wait for
         hpv_mbar_wait(&bar[ch], phase);
+#endif
         hpv_tc_fence_after();
         float v[HPH];
         hpv_tmem_ld_n<HPH>(tb_lane + ch * HPV_TC_NPAD + u0, v);
@@ -210,13 +212,16 @@ __device__ __forceinline__ void hpv_mlpbwd_tc_body(const HpvCta& c, const HpvBwd
     uint32_t phase = 0;
 
     auto issue = [&](int tile_index) {
+#if defined(HPV_EXP_NO_MMA)
+        if (tile_index >= 0) return;
+#endif
         if (warp == 0) {
             hpv_tc_fence_after();
             if (hpv_elect_one()) {
                 const uint32_t bhi = hpv_smem_u32(s_B) + (uint32_t)tile_index * (uint32_t)(L.B_layer * 4);
                 const uint32_t blo = bhi + (uint32_t)(KP * HPV_TC_NPAD * 4);
-                if (TCOLS == 512u || tb == 0u) hpv_tc_issue_layer<0, NCH, KP>(bhi, blo, s_bar);
-                else hpv_tc_issue_layer<256, NCH, KP>(bhi, blo, s_bar);
+                if (TCOLS == 512u || tb == 0u) hpv_tc_issue_layer<0, NCH, KP, HpvTcDims<HP>::NMMA>(bhi, blo, s_bar);
+                else hpv_tc_issue_layer<256, NCH, KP, HpvTcDims<HP>::NMMA>(bhi, blo, s_bar);
             }
             __syncwarp();
         }

@@ -173,8 +173,8 @@ __device__ __forceinline__ void hpv_mlpbwd_tcw_body(const HpvCta& c, const HpvBw
             if (hpv_elect_one()) {
                 const uint32_t bhi = hpv_smem_u32(s_B) + (uint32_t)tile_index * (uint32_t)(L.B_layer * 4);
                 const uint32_t blo = bhi + (uint32_t)(KP * HPV_TC_NPAD * 4);
-                if (tb == 0u) hpv_tc_issue_layer<0, NCH, KP>(bhi, blo, s_bar);
-                else hpv_tc_issue_layer<256, NCH, KP>(bhi, blo, s_bar);
+                if (tb == 0u) hpv_tc_issue_layer<0, NCH, KP, HpvTcDims<HP>::NMMA>(bhi, blo, s_bar);
+                else hpv_tc_issue_layer<256, NCH, KP, HpvTcDims<HP>::NMMA>(bhi, blo, s_bar);
             }
             __syncwarp();
         }

@@ -2,7 +2,7 @@
 // net_u and input derivatives at the tensor Gauss-Lobatto points (P2D:81-83,158-185), projection on the test
 // functions by sum factorisation (P2D:94-115), Res = U - F_ext, element loss, lossv (P2D:118-120) -- with
 //   * the hidden-layer products of the MLP on the 5th-generation tensor cores: tcgen05.mma kind::tf32, M = 128
-//     quadrature points, N = 32 (output units, padded), K = 8 per instruction; the activations of a layer are the A
+//     quadrature points, N = 16 / 24 / 32 (output units, padded), K = 8 per instruction; the activations of a layer are the A
 //     operand and live in tensor memory (TMEM), written there by the threads that computed them (tcgen05.st); the
 //     weights with the bias as an extra input row are K-major B tiles in shared memory; the pre-activations of the
 //     next layer accumulate in TMEM and come back with tcgen05.ld.  fp32-class accuracy from TF32 products by the
@@ -27,6 +27,12 @@
 template <int HP> struct HpvTcDims {
     static constexpr int KP = ((HP + 1 + 7) / 8) * 8;          // inputs + bias row, padded to the instruction's K = 8
     static constexpr int HPH = HP / 2;                         // units per thread
+    // N of the MMA instruction: the output units rounded up to 8, at least 16.  (N = 24 with M = 128 is outside the
+    // N % 16 == 0 rule the PTX manual states for M = 128, but the instruction descriptor carries N >> 3 and the
+    // hardware runs it: tools/probes/umma_probe.cu test 3 is exact against the reference at N = 24, at 16.4 instead of
+    // 19.9 cycles per instruction; every parity test runs through it.  The tiles in shared and tensor memory keep
+    // their 32-row / 32-column pitch.)
+    static constexpr int NMMA = HP <= 16 ? 16 : (HP <= 24 ? 24 : HPV_TC_NPAD);
 };
 // TMEM columns of a CTA: NCH accumulators of NPAD columns, then the A operands (hi, then lo; KP columns per channel).
 HPV_HD constexpr int hpv_tc_tmem_need(int nch, int hp) { return nch * HPV_TC_NPAD + 2 * nch * (((hp + 1 + 7) / 8) * 8); }
@@ -143,10 +149,10 @@ __device__ __forceinline__ void hpv_tc_split_store(uint32_t addr_hi, uint32_t ad
 // so every operand sits in a uniform register without a transfer from the vector registers: the instructions go out
 // back to back (tools/probes/umma_probe.cu, tests 10 and 13: 17-20 cycles per instruction against 90-190 with
 // operands that have to be moved per instruction).
-template <uint32_t TB, int NCH, int KP>
+template <uint32_t TB, int NCH, int KP, int NMMA>
 __device__ __forceinline__ void hpv_tc_issue_layer(uint32_t bhi, uint32_t blo, uint64_t* bar) {
     constexpr uint32_t colD = 0, colAhi = NCH * HPV_TC_NPAD, colAlo = colAhi + NCH * KP;
-    constexpr uint32_t idesc = hpv_umma_idesc_tf32(HPV_TC_MTILE, HPV_TC_NPAD, 0, 0);
+    constexpr uint32_t idesc = hpv_umma_idesc_tf32(HPV_TC_MTILE, NMMA, 0, 0);
     constexpr uint32_t LBO = HPV_TC_NPAD * 16, SBO = 128;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
@@ -366,14 +372,18 @@ __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVar
                 if (l > 1) {
                     // pre-activations of hidden layer l from TMEM, channel by channel as the products complete
                     hpv_each_ch_s<M>(s, [&](float* zp, int ch) {
+#if !defined(HPV_EXP_NO_MMA)          // timing experiment only (tools/gpu_r2l.sh)
                         hpv_mbar_wait(&s_bar[ch], phase);
+#endif
                         hpv_tc_fence_after();
                         hpv_tmem_ld_n<HPH>(tb + lane_base + colD + ch * HPV_TC_NPAD + u0, zp);
                         hpv_tmem_wait_ld();
                     });
                     phase ^= 1;
                 }
+#if !defined(HPV_EXP_NO_ACT)          // timing experiment only (tools/gpu_r2l.sh)
                 hpv_activate_s<DIM, MX, MY, HPH, ACT>(s);                // post-activations h, dh, d2h of layer l
+#endif
                 if (l == nhid) break;
                 // split and store as the A operand of the next product
                 hpv_each_ch_s<M>(s, [&](float* hp_, int ch) {
@@ -382,16 +392,18 @@ __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVar
                 hpv_tmem_wait_st();
                 hpv_tc_fence_before();
                 __syncthreads();
+#if !defined(HPV_EXP_NO_MMA)
                 if (warp == 0) {
                     hpv_tc_fence_after();
                     if (hpv_elect_one()) {
                         const uint32_t bhi = hpv_smem_u32(s_B) + (uint32_t)(l - 1) * (uint32_t)(L.B_layer * 4);
                         const uint32_t blo = bhi + (uint32_t)(KP * HPV_TC_NPAD * 4);
-                        if (TCOLS == 512u || tb == 0u) hpv_tc_issue_layer<0, NCH, KP>(bhi, blo, s_bar);
-                        else hpv_tc_issue_layer<256, NCH, KP>(bhi, blo, s_bar);
+                        if (TCOLS == 512u || tb == 0u) hpv_tc_issue_layer<0, NCH, KP, HpvTcDims<HP>::NMMA>(bhi, blo, s_bar);
+                        else hpv_tc_issue_layer<256, NCH, KP, HpvTcDims<HP>::NMMA>(bhi, blo, s_bar);
                     }
                     __syncwarp();
                 }
+#endif
             }
             // output layer: partial sums over this thread's units, combined across the two halves
             {
@@ -430,6 +442,7 @@ __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVar
         hpv_sync(c);
 
         // (3) first contraction, over the x index:  P_t[jl][r] = c_t * sum_i G_t[jl][i] * R_t[i][r]
+#if !defined(HPV_EXP_NO_PROJ)             // timing experiment only (tools/gpu_r2l.sh)
         {
             const int ng = (nrows + 3) >> 2;
             const int nitems = a.n_terms * ng * (HPV_NP / 4);
@@ -483,6 +496,7 @@ __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVar
                     for (int j = 0; j < 4; ++j) U[i][j] = fmaf(ls[i], ps[j], U[i][j]);
             }
         }
+#endif
 
         t_cur += nt;
         if (t_cur == t_end || t_cur % tpe == 0) {
