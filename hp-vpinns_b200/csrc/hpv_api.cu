@@ -114,7 +114,7 @@ struct hpv_ctx {
     bool bwd_tcw = false;              // ... with the weight gradients on the tensor cores too (HPV_BWD_TCW=1; measured slower and
                                        // less accurate than the FMA-pipe weight gradients: DESIGN.md, kept for A/B measurements)
     bool bwd_tcw_active = false;
-    int fwd_ctas_per_sm = 0, adj_grid = 0, slabs_per_el = 0;
+    int fwd_ctas_per_sm = 0, adj_grid = 0, slabs_per_el = 0, part_tile = HPV_FWD_TILE;
     PointSet ps[HPV_MAX_POINT_SETS];
     // training configuration
     double wv = 1.0; unsigned mask = 0; int train_eps = 0;
@@ -213,7 +213,7 @@ void fill_var_args(hpv_ctx* c, HpvVarArgs& a) {
     a.F = c->has_F ? c->F.p : nullptr;
     a.n_terms = c->form.n_terms;
     for (int t = 0; t < HPV_MAX_TERMS; ++t) a.terms[t] = c->form.terms[t];
-    a.tiles_per_el = c->part.tiles_per_el; a.n_ctas = c->part.n_ctas;
+    a.tile_pts = c->part_tile; a.tiles_per_el = c->part.tiles_per_el; a.n_ctas = c->part.n_ctas;
     a.cta_tile_begin = c->cta_tile_begin.p; a.el_first_cta = c->el_first_cta.p;
     a.el_part_off = c->el_part_off.p; a.el_nparts = c->el_nparts.p;
     a.Upart = c->Upart.p; a.el_done = c->counters.p; a.n_done = c->counters.p + c->n_el;
@@ -347,7 +347,9 @@ int ensure_ready(hpv_ctx* c) {
         c->fwd_ctas_per_sm = (int)out;
     }
     const int rows = (c->net.dim == 2) ? c->Q : 1;
-    hpv_partition(c->part, c->n_el, rows * c->Q, HPV_FWD_TILE, c->n_sm * c->fwd_ctas_per_sm, HPV_THREADS);
+    // tiles of one MMA tile (128 points) for the tensor-core form: 10 or 11 per CTA at C3 instead of 5 or 6 of 256
+    c->part_tile = c->fwd_tc_active ? HPV_TC_MTILE : HPV_FWD_TILE;
+    hpv_partition(c->part, c->n_el, rows * c->Q, c->part_tile, c->n_sm * c->fwd_ctas_per_sm, c->fwd_tc_active ? 0 : HPV_THREADS);
     { int r;
       if ((r = upload(c, c->cta_tile_begin, c->part.cta_tile_begin))) return r;
       if ((r = upload(c, c->el_first_cta, c->part.el_first_cta))) return r;
@@ -405,10 +407,14 @@ int ensure_ready(hpv_ctx* c) {
     return HPV_OK;
 }
 
-int launch_forward(hpv_ctx* c) {
+// defer_total: the sum of the element losses is left to the loss assembly of the step's gradient reduction
+// (hpv_losses_warp) instead of the forward kernel's very last CTA -- two fences and an atomic off the critical path of
+// every element's last CTA
+int launch_forward(hpv_ctx* c, bool defer_total = false) {
     // the tensor-core form reads the parameters from global memory (theta_pad), not from the constant-memory mirror
     if (!c->fwd_tc_active) { int r = refresh_mirror(c, HPV_K_VARFWD); if (r) return r; }
     HpvVarArgs a; fill_var_args(c, a);
+    a.defer_total = defer_total ? 1 : 0;
     HpvLaunch l; memset(&l, 0, sizeof(l));
     l.kind = c->fwd_tc_active ? HPV_K_VARFWD_TC : HPV_K_VARFWD; l.op = 0; l.grid = c->part.n_ctas; l.block = HPV_THREADS; l.smem = c->fwd_smem;
     l.stream = c->stream; l.var = &a;
@@ -1028,7 +1034,7 @@ static int loss_and_grad_impl(hpv_ctx* c, bool fuse_adam, bool device_hist = fal
     // the last one of the step also assembles the loss values (saves a launch).
     int acc = 0, pending = -1;
     if (use_v) {
-        int r = launch_forward(c);
+        int r = launch_forward(c, true);
         if (!r) r = launch_adjproj(c);
         if (!r) r = launch_mlpbwd_var(c);
         if (r) return r;
@@ -1036,6 +1042,7 @@ static int loss_and_grad_impl(hpv_ctx* c, bool fuse_adam, bool device_hist = fal
     }
     HpvLossArgs la; memset(&la, 0, sizeof(la));
     la.lossv = c->loss.p; la.wv = (float)c->wv; la.use_v = use_v ? 1 : 0; la.out = c->redbuf.p + c->loss_off;
+    if (use_v) { la.el_loss = c->el_loss.p; la.n_el = c->n_el; }     // the forward kernel left the total to the loss assembly
     if (device_hist) {
         la.hist = c->hist_ring.p; la.hist_cap = HPV_HIST_CAP; la.hist_t0 = c->hist_t0.p;
         la.clock = c->adam_clock.p + 3 * c->adam_parity;           // the clock buffer this step's update reads
@@ -1362,14 +1369,14 @@ int hpv_time_kernel(hpv_ctx* c, int what, int reps, double* usec) {
     HPV_CK(cudaSetDevice(c->device));
     { int r = ensure_ready(c); if (r) return r; }
     auto run = [&]() -> int {
-        if (what == 0) return launch_forward(c);
+        if (what == 0) return launch_forward(c, true);        // as the training step launches it
         if (what == 1) return launch_adjproj(c);
         if (what == 2) return launch_mlpbwd_var(c);
         int r = launch_gradreduce(c, c->bwd_grid, 0);
         if (!r) r = unpad_grad(c, 0);
         return r;
     };
-    if (what >= 1) { int r = launch_forward(c); if (r) return r; }
+    if (what >= 1) { int r = launch_forward(c, true); if (r) return r; }
     if (what >= 2) { int r = launch_adjproj(c); if (r) return r; }
     if (what >= 3) { int r = launch_mlpbwd_var(c); if (r) return r; }
     for (int i = 0; i < 3; ++i) { int r = run(); if (r) return r; }

@@ -92,10 +92,22 @@ struct HpvLossArgs {
     // optional device-side loss history (graph-replayed training steps cannot take a per-step destination from the
     // host): the values also go to hist[8 * (t - t0)] with t the optimizer's step counter (clock[2]) -- 0 <= t - t0 < hist_cap
     float* hist; const double* clock; const double* hist_t0; int hist_cap;
+    // non-null: lossv is the sum of these element losses (float64, fixed order), formed here instead of in the forward kernel
+    const float* el_loss; int n_el;
 };
 #if defined(__CUDACC__)
 __device__ inline void hpv_losses_warp(const HpvLossArgs& a, int lane) {
-    const float lv = a.use_v ? (float)a.lossv[0] : 0.0f;
+    float lv = 0.0f;
+    if (a.use_v) {
+        if (a.el_loss) {
+            double acc = 0.0;
+            for (int i = lane; i < a.n_el; i += 32) acc += (double)a.el_loss[i];
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            lv = (float)acc;
+        } else {
+            lv = (float)a.lossv[0];
+        }
+    }
     float total = a.wv * lv;
     float pl[HPV_MAX_POINT_SETS];
     for (int s = 0; s < HPV_MAX_POINT_SETS; ++s) {

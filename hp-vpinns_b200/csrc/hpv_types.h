@@ -52,7 +52,9 @@ struct HpvVarArgs {
     // terms
     int n_terms;
     HpvTerm terms[HPV_MAX_TERMS];
-    // work partition (point tiles of HPV_THREADS points, never straddling elements)
+    // work partition (point tiles of tile_pts points, never straddling elements; tile_pts = HPV_FWD_TILE for the FFMA
+    // forward kernel, 128 = one MMA tile for the tensor-core form: finer tiles, better balance over the CTAs)
+    int tile_pts;
     int tiles_per_el;
     int n_ctas;
     const int* cta_tile_begin; // [n_ctas+1]
@@ -72,6 +74,7 @@ struct HpvVarArgs {
     float* grad_pad;           // [theta_pad_n + 4] reduced gradient in the padded layout
     unsigned int* bwd_done;    // [1]
     float loss_scale;          // multiplies the adjoint (1 for lossv)
+    int defer_total;           // != 0: the forward kernel writes el_loss only; loss[0] is not formed (see hpv_losses_warp)
 };
 
 // Scattered-point evaluation (net_u and derivatives; boundary / PINN losses).

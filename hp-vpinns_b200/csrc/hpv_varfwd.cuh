@@ -103,15 +103,15 @@ HPV_HD void hpv_varfwd_body(const HpvCta& c, const HpvVarArgs& a) {
     int t_cur = a.cta_tile_begin[c.bid];
     const int t_end = a.cta_tile_begin[c.bid + 1];
 
-    // The partition counts tiles of HPV_FWD_TILE points; a chunk's last pass may leave warps without points.
-    constexpr int CHUNK_TILES = HPV_CT * HPV_THREADS / HPV_FWD_TILE;
+    // The partition counts tiles of a.tile_pts points; a chunk's last pass may leave warps without points.
+    const int tile_pts = a.tile_pts, CHUNK_TILES = HPV_CT * HPV_THREADS / tile_pts;
     while (t_cur < t_end) {
         const int e = t_cur / tpe, k0 = t_cur - e * tpe;
         int nt = tpe - k0;
         if (nt > CHUNK_TILES) nt = CHUNK_TILES;
         if (nt > t_end - t_cur) nt = t_end - t_cur;
-        const int p0 = k0 * HPV_FWD_TILE;
-        int p1 = (k0 + nt) * HPV_FWD_TILE;
+        const int p0 = k0 * tile_pts;
+        int p1 = (k0 + nt) * tile_pts;
         if (p1 > npts_el) p1 = npts_el;
         const int npass = (p1 - p0 + T - 1) / T;
         const int ja = p0 / Q, jb = (p1 - 1) / Q, nrows = jb - ja + 1, base = ja * Q;
@@ -273,26 +273,31 @@ HPV_HD void hpv_varfwd_body(const HpvCta& c, const HpvVarArgs& a) {
                 if (tid == 0) {
                     a.el_loss[e] = tot / (float)(ntx_e * nty_e);
                     a.el_done[e] = 0u;
-                    hpv_fence();
-                    unsigned int prev = hpv_atomic_inc(a.n_done);
-                    s_flag[1] = (prev == (unsigned int)(a.n_el - 1)) ? 1 : 0;
                 }
-                hpv_sync(c);
-                if (s_flag[1]) {
-                    // (6) every element is finished: lossv = sum of the element losses (P2D:120), fixed order
-                    hpv_fence();
-                    double* dred = reinterpret_cast<double*>(s_red);
-                    double acc = 0.0;
-                    for (int i = tid; i < a.n_el; i += T) acc += (double)hpv_ld_cg(a.el_loss + i);
-                    dred[tid] = acc;
-                    hpv_sync(c);
-                    for (int s = T >> 1; s > 0; s >>= 1) {
-                        if (tid < s) dred[tid] += dred[tid + s];
-                        hpv_sync(c);
+                // the sum over the elements: by the very last CTA, unless the step's loss assembly forms it (defer_total)
+                if (!a.defer_total) {
+                    if (tid == 0) {
+                        hpv_fence();
+                        unsigned int prev = hpv_atomic_inc(a.n_done);
+                        s_flag[1] = (prev == (unsigned int)(a.n_el - 1)) ? 1 : 0;
                     }
-                    if (tid == 0) { a.loss[0] = dred[0]; a.n_done[0] = 0u; }
+                    hpv_sync(c);
+                    if (s_flag[1]) {
+                        // (6) every element is finished: lossv = sum of the element losses (P2D:120), fixed order
+                        hpv_fence();
+                        double* dred = reinterpret_cast<double*>(s_red);
+                        double acc = 0.0;
+                        for (int i = tid; i < a.n_el; i += T) acc += (double)hpv_ld_cg(a.el_loss + i);
+                        dred[tid] = acc;
+                        hpv_sync(c);
+                        for (int s = T >> 1; s > 0; s >>= 1) {
+                            if (tid < s) dred[tid] += dred[tid + s];
+                            hpv_sync(c);
+                        }
+                        if (tid == 0) { a.loss[0] = dred[0]; a.n_done[0] = 0u; }
+                    }
+                    hpv_sync(c);
                 }
-                hpv_sync(c);
             }
         }
         hpv_sync(c);

@@ -74,6 +74,25 @@ HPV_HD HpvFwdTcSmem hpv_fwd_tc_smem(const HpvVarArgs& a, int dim, int hp, int nc
 
 #if defined(__CUDACC__)
 
+#if defined(HPV_EXP_STAMPS)
+// Timing experiment only (tools/gpu_r2q.sh): thread 0 of every CTA of the forward kernel records %globaltimer at the
+// phase boundaries and the time it spent in each phase; read back with hpv_exp_read_stamps (hpv_k_h20_fwdtc.cu).
+#define HPV_EXP_NSTAMP 12
+static __device__ unsigned long long hpv_exp_stamps[1024 * HPV_EXP_NSTAMP];
+__device__ __forceinline__ unsigned long long hpv_exp_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define HPV_STAMP(i) do { if (tid == 0 && c.bid < 1024) hpv_exp_stamps[c.bid * HPV_EXP_NSTAMP + (i)] = hpv_exp_now(); } while (0)
+#define HPV_STAMP_BEGIN(v) unsigned long long v = (tid == 0) ? hpv_exp_now() : 0ull
+#define HPV_STAMP_ADD(i, v) do { if (tid == 0 && c.bid < 1024) hpv_exp_stamps[c.bid * HPV_EXP_NSTAMP + (i)] += hpv_exp_now() - v; } while (0)
+#else
+#define HPV_STAMP(i) do { } while (0)
+#define HPV_STAMP_BEGIN(v) do { } while (0)
+#define HPV_STAMP_ADD(i, v) do { } while (0)
+#endif
+
 __device__ __forceinline__ bool hpv_elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
@@ -220,6 +239,20 @@ __device__ __forceinline__ void hpv_tc_split_store_s(uint32_t addr_hi, uint32_t 
     hpv_tmem_st_n<N>(addr_lo, lo);
 }
 
+// Deterministic block-wide sum with two barriers: xor-shuffle tree inside each warp, then every thread adds the warps'
+// sums in warp order (hpv_block_sum's shared-memory tree costs ten barriers; this sits on the critical path of every
+// element's last CTA).  `red` holds one float per warp.
+__device__ __forceinline__ float hpv_block_sum_warps(const HpvCta& c, float* red, float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    hpv_sync(c);                                   // an earlier use of `red` may still be read
+    if ((c.tid & 31) == 0) red[c.tid >> 5] = v;
+    hpv_sync(c);
+    float r = 0.0f;
+    for (int w = 0; w < (c.nthreads >> 5); ++w) r += red[w];
+    return r;
+}
+
 template <int DIM, int MX, int MY, int HP, int ACT>
 __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVarArgs& a) {
     typedef HpvMode<DIM, MX, MY> M;
@@ -244,6 +277,10 @@ __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVar
     const int prow = sub * 32 + lane;
 
     // ---- one-time set-up: TMEM, mbarriers, tables by TMA, parameters, weight tiles ----
+#if defined(HPV_EXP_STAMPS)
+    if (tid == 0 && c.bid < 1024) for (int i = 0; i < HPV_EXP_NSTAMP; ++i) hpv_exp_stamps[c.bid * HPV_EXP_NSTAMP + i] = 0ull;
+#endif
+    HPV_STAMP(0);
     if (warp == 0) hpv_tmem_alloc(s_tbase, TCOLS);
     if (tid == 0) {
         for (int i = 0; i <= HPV_NFIELDS; ++i) hpv_mbar_init(&s_bar[i], 1);
@@ -306,7 +343,9 @@ __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVar
         }
         hpv_tmem_wait_st();
     }
+    HPV_STAMP(1);
     hpv_mbar_wait(&s_bar[HPV_NFIELDS], 0);      // tables have landed
+    HPV_STAMP(2);
 
     const int kt = tid >> 4, rt = tid & 15;
     float U[4][4];
@@ -324,14 +363,14 @@ __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVar
     const float* b1 = s_th + DIM * HP;
     const float* Wo = s_th + (DIM + 1) * HP;
 
-    constexpr int CHUNK_TILES = HPV_CT * HPV_THREADS / HPV_FWD_TILE;
+    const int tile_pts = a.tile_pts, CHUNK_TILES = HPV_CT * HPV_THREADS / tile_pts;
     while (t_cur < t_end) {
         const int e = t_cur / tpe, k0 = t_cur - e * tpe;
         int nt = tpe - k0;
         if (nt > CHUNK_TILES) nt = CHUNK_TILES;
         if (nt > t_end - t_cur) nt = t_end - t_cur;
-        const int p0 = k0 * HPV_FWD_TILE;
-        int p1 = (k0 + nt) * HPV_FWD_TILE;
+        const int p0 = k0 * tile_pts;
+        int p1 = (k0 + nt) * tile_pts;
         if (p1 > npts_el) p1 = npts_el;
         const int nmt = (p1 - p0 + HPV_TC_MTILE - 1) / HPV_TC_MTILE;            // MMA tiles of 128 points in this chunk
         const int ja = p0 / Q, jb = (p1 - 1) / Q, nrows = jb - ja + 1, base = ja * Q;
@@ -344,6 +383,7 @@ __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVar
         // (no barrier needed here: the first barrier of the MLP phase below orders the clears before the field stores)
 
         // (2) network and input derivatives at the quadrature points, 128 points at a time
+        HPV_STAMP_BEGIN(ts_mlp);
 #pragma unroll 1
         for (int mt = 0; mt < nmt; ++mt) {
             const int p = p0 + mt * HPV_TC_MTILE + prow;
@@ -440,6 +480,8 @@ __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVar
             }
         }
         hpv_sync(c);
+        HPV_STAMP_ADD(5, ts_mlp);
+        HPV_STAMP_BEGIN(ts_p3);
 
         // (3) first contraction, over the x index:  P_t[jl][r] = c_t * sum_i G_t[jl][i] * R_t[i][r]
 #if !defined(HPV_EXP_NO_PROJ)             // timing experiment only (tools/gpu_r2l.sh)
@@ -481,6 +523,8 @@ __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVar
             }
         }
         hpv_sync(c);
+        HPV_STAMP_ADD(6, ts_p3);
+        HPV_STAMP_BEGIN(ts_p4);
 
         // (4) second contraction, over the y index:  U[k][r] += sum_t sum_jl L_t[ja+jl][k] * P_t[jl][r]
         for (int t = 0; t < a.n_terms; ++t) {
@@ -498,6 +542,8 @@ __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVar
         }
 #endif
 
+        HPV_STAMP_ADD(7, ts_p4);
+        HPV_STAMP_BEGIN(ts_fin);
         t_cur += nt;
         if (t_cur == t_end || t_cur % tpe == 0) {
             // (5) done with element e: publish the partial U; the last part to arrive reduces the parts in a fixed
@@ -511,6 +557,17 @@ __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVar
                 hpv_st4(up + (4 * kt + i) * HPV_NP + 4 * rt, o);
                 U[i][0] = U[i][1] = U[i][2] = U[i][3] = 0.0f;
             }
+            // this thread's entries of the right-hand side, fetched while the arrival counter makes its round trip (only
+            // the last CTA to arrive uses them: a latency taken off the critical path of the element's last part)
+            const int ntx_e = a.el_ntest[2 * e + 0], nty_e = a.el_ntest[2 * e + 1];
+            float Fv[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = 4 * kt + i, r = 4 * rt + j;
+                    Fv[i][j] = (a.F && k < nty_e && r < ntx_e) ? a.F[((size_t)e * a.nty + k) * a.ntx + r] : 0.0f;
+                }
             hpv_fence();
             hpv_sync(c);
             if (tid == 0) {
@@ -520,7 +577,6 @@ __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVar
             hpv_sync(c);
             if (s_flag[0]) {
                 hpv_fence();
-                const int ntx_e = a.el_ntest[2 * e + 0], nty_e = a.el_ntest[2 * e + 1];
                 float S[4][4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -544,7 +600,7 @@ __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVar
                         const int r = 4 * rt + j;
                         if (k < nty_e && r < ntx_e) {
                             const size_t idx = ((size_t)e * a.nty + k) * a.ntx + r;
-                            const float res = S[i][j] - (a.F ? a.F[idx] : 0.0f);
+                            const float res = S[i][j] - Fv[i][j];
                             a.Res[idx] = res;
                             sq = fmaf(res, res, sq);
                         } else if (k < a.nty && r < a.ntx) {
@@ -552,37 +608,45 @@ __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVar
                         }
                     }
                 }
-                const float tot = hpv_block_sum(c, s_red, sq);
+                const float tot = hpv_block_sum_warps(c, s_red, sq);
                 if (tid == 0) {
                     a.el_loss[e] = tot / (float)(ntx_e * nty_e);
                     a.el_done[e] = 0u;
-                    hpv_fence();
-                    unsigned int prev = hpv_atomic_inc(a.n_done);
-                    s_flag[1] = (prev == (unsigned int)(a.n_el - 1)) ? 1 : 0;
                 }
-                hpv_sync(c);
-                if (s_flag[1]) {
-                    hpv_fence();
-                    double* dred = reinterpret_cast<double*>(s_red);
-                    double acc = 0.0;
-                    for (int i = tid; i < a.n_el; i += T) acc += (double)hpv_ld_cg(a.el_loss + i);
-                    dred[tid] = acc;
-                    hpv_sync(c);
-                    for (int sft = T >> 1; sft > 0; sft >>= 1) {
-                        if (tid < sft) dred[tid] += dred[tid + sft];
-                        hpv_sync(c);
+                // the sum over the elements: by the very last CTA, unless the step's loss assembly forms it (defer_total)
+                if (!a.defer_total) {
+                    if (tid == 0) {
+                        hpv_fence();
+                        unsigned int prev = hpv_atomic_inc(a.n_done);
+                        s_flag[1] = (prev == (unsigned int)(a.n_el - 1)) ? 1 : 0;
                     }
-                    if (tid == 0) { a.loss[0] = dred[0]; a.n_done[0] = 0u; }
+                    hpv_sync(c);
+                    if (s_flag[1]) {
+                        hpv_fence();
+                        double* dred = reinterpret_cast<double*>(s_red);
+                        double acc = 0.0;
+                        for (int i = tid; i < a.n_el; i += T) acc += (double)hpv_ld_cg(a.el_loss + i);
+                        dred[tid] = acc;
+                        hpv_sync(c);
+                        for (int sft = T >> 1; sft > 0; sft >>= 1) {
+                            if (tid < sft) dred[tid] += dred[tid + sft];
+                            hpv_sync(c);
+                        }
+                        if (tid == 0) { a.loss[0] = dred[0]; a.n_done[0] = 0u; }
+                    }
+                    hpv_sync(c);
                 }
-                hpv_sync(c);
             }
         }
         hpv_sync(c);
+        HPV_STAMP_ADD(8, ts_fin);
     }
+    HPV_STAMP(3);
     hpv_pdl_trigger();
     hpv_tc_fence_before();
     __syncthreads();
     if (warp == 0) hpv_tmem_dealloc(tb, TCOLS);
+    HPV_STAMP(4);
 }
 
 #endif  // __CUDACC__

@@ -223,7 +223,7 @@ int hpv_emu_varloss(int dim, const int* layers, int n_layers, int act, int Q, co
     a.F = fm.has_rhs && F_ext ? F.data() : nullptr;
     a.n_terms = fm.n_terms;
     for (int t = 0; t < HPV_MAX_TERMS; ++t) a.terms[t] = fm.terms[t];
-    a.tiles_per_el = part.tiles_per_el; a.n_ctas = part.n_ctas;
+    a.tile_pts = HPV_FWD_TILE; a.tiles_per_el = part.tiles_per_el; a.n_ctas = part.n_ctas;
     a.cta_tile_begin = part.cta_tile_begin.data(); a.el_first_cta = part.el_first_cta.data();
     a.el_part_off = part.el_part_off.data(); a.el_nparts = part.el_nparts.data();
     a.Upart = Upart.data(); a.el_done = counters.data(); a.n_done = counters.data() + n_el;
