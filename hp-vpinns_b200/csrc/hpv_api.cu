@@ -349,7 +349,20 @@ int ensure_ready(hpv_ctx* c) {
     const int rows = (c->net.dim == 2) ? c->Q : 1;
     // tiles of one MMA tile (128 points) for the tensor-core form: 10 or 11 per CTA at C3 instead of 5 or 6 of 256
     c->part_tile = c->fwd_tc_active ? HPV_TC_MTILE : HPV_FWD_TILE;
-    hpv_partition(c->part, c->n_el, rows * c->Q, c->part_tile, c->n_sm * c->fwd_ctas_per_sm, c->fwd_tc_active ? 0 : HPV_THREADS);
+    {
+        // cost model of the tensor-core form (fitted to per-CTA phase timings at C3, profiles/round2_tuning/
+        // varfwd_tc_cta_timeline.txt): an element boundary inside a CTA's range costs about 2.4 tiles, the second CTA of
+        // an SM runs its tiles 16 % slower than the first.  HPV_FWD_BALANCE=0 switches the weighting off.
+        HpvPartitionCost pc;
+        const char* ev = getenv("HPV_FWD_BALANCE");
+        if (c->fwd_tc_active && !(ev && atoi(ev) == 0)) {
+            const long long ntiles = (long long)c->n_el * ((rows * c->Q + c->part_tile - 1) / c->part_tile);
+            const double avg = (double)ntiles / (double)(c->n_sm * c->fwd_ctas_per_sm);
+            pc.cross = avg >= 8.0 ? 2.4 : 0.3 * avg;
+            if (c->fwd_ctas_per_sm == 2) { pc.first_wave = c->n_sm; pc.wave2 = 1.16; }
+        }
+        hpv_partition(c->part, c->n_el, rows * c->Q, c->part_tile, c->n_sm * c->fwd_ctas_per_sm, c->fwd_tc_active ? 0 : HPV_THREADS, &pc);
+    }
     { int r;
       if ((r = upload(c, c->cta_tile_begin, c->part.cta_tile_begin))) return r;
       if ((r = upload(c, c->el_first_cta, c->part.el_first_cta))) return r;

@@ -187,9 +187,21 @@ struct HpvPartition {
     std::vector<int> cta_tile_begin, el_first_cta, el_part_off, el_nparts;
 };
 
+// Cost model of a CTA's share for the weighted partition (all in units of one tile's run time): a tile costs 1 on the
+// first `first_wave` CTAs and `wave2` on the others (the second CTA an SM takes gets fewer issue slots than the first),
+// every element boundary inside a CTA's range costs `cross` (one more chunk, one more partial-U publication, and such a
+// CTA is usually the last to arrive at the element it finishes).  cross = 0, wave2 = 1: equal tile counts.
+struct HpvPartitionCost {
+    double cross = 0.0;
+    int first_wave = 0;
+    double wave2 = 1.0;
+};
+
 // Tiles of tile_pts points (never straddling elements), a contiguous range of tiles per CTA; a CTA gets at least
-// cta_pts points' worth of tiles (one full pass of its threads) unless there is less work than that.
-inline void hpv_partition(HpvPartition& p, int n_el, int pts_per_el, int tile_pts, int max_ctas, int cta_pts = 0) {
+// cta_pts points' worth of tiles (one full pass of its threads) unless there is less work than that.  With a cost
+// model the ranges are chosen so that the modelled costs of the CTAs are (nearly) equal.
+inline void hpv_partition(HpvPartition& p, int n_el, int pts_per_el, int tile_pts, int max_ctas, int cta_pts = 0,
+                          const HpvPartitionCost* cost = nullptr) {
     p.tiles_per_el = (pts_per_el + tile_pts - 1) / tile_pts;
     const long long ntiles = (long long)n_el * p.tiles_per_el;
     const long long per_cta = cta_pts > tile_pts ? cta_pts / tile_pts : 1;
@@ -198,6 +210,34 @@ inline void hpv_partition(HpvPartition& p, int n_el, int pts_per_el, int tile_pt
     if (p.n_ctas < 1) p.n_ctas = 1;
     p.cta_tile_begin.resize(p.n_ctas + 1);
     for (int c = 0; c <= p.n_ctas; ++c) p.cta_tile_begin[c] = (int)((ntiles * c) / p.n_ctas);
+    if (cost && (cost->cross > 0.0 || cost->wave2 != 1.0) && ntiles > p.n_ctas) {
+        const int n = p.n_ctas, tpe = p.tiles_per_el;
+        // Greedy in CTA order with a target that is re-derived from what is left (so rounding does not pile up at the end
+        // of the list): equal run times T mean tiles_c = (T - cross * k_c) / alpha_c, hence for the CTAs c .. n-1
+        //   T = (tiles left + cross * boundaries left / alpha) / sum 1 / alpha_c';  a CTA takes tiles up to the cost
+        // nearest to T, at least one, and leaves one for each later CTA; the last CTA takes the rest.
+        std::vector<int> begin(n + 1);
+        std::vector<double> inv_tail(n + 1, 0.0);                  // sum over c' >= c of 1 / alpha_c'
+        auto alpha_of = [&](int c) { return (cost->first_wave > 0 && c >= cost->first_wave) ? cost->wave2 : 1.0; };
+        for (int c = n - 1; c >= 0; --c) inv_tail[c] = inv_tail[c + 1] + 1.0 / alpha_of(c);
+        long long t = 0;
+        for (int c = 0; c < n; ++c) {
+            begin[c] = (int)t;
+            const double alpha = alpha_of(c);
+            const long long left = ntiles - t;
+            const long long bounds_left = (ntiles - 1) / tpe - t / tpe;       // element starts strictly after tile t
+            const double mean_alpha = (double)(n - c) / inv_tail[c];
+            const double T = ((double)left + cost->cross * (double)bounds_left / mean_alpha) / inv_tail[c];
+            double acc = 0.0;
+            while (t < ntiles && (c == n - 1 || ntiles - t > (long long)(n - c - 1))) {
+                const double add = alpha + ((t % tpe == 0 && t != begin[c]) ? cost->cross : 0.0);
+                if (c < n - 1 && acc + 0.5 * add > T && t > begin[c]) break;
+                acc += add; ++t;
+            }
+        }
+        begin[n] = (int)ntiles;
+        p.cta_tile_begin = begin;
+    }
     p.el_first_cta.assign(n_el, 0);
     p.el_nparts.assign(n_el, 0);
     p.el_part_off.assign(n_el, 0);

@@ -144,6 +144,17 @@ int hpv_emu_partition(int n_el, int pts_per_el, int tile_pts, int max_ctas, int 
     return p.n_ctas;
 }
 
+// the same with the cost model of the tensor-core forward kernel's launch plan
+int hpv_emu_partition_weighted(int n_el, int pts_per_el, int tile_pts, int max_ctas, double cross, int first_wave, double wave2,
+                               int* tiles_per_el, int* cta_tile_begin) {
+    HpvPartition p;
+    HpvPartitionCost pc; pc.cross = cross; pc.first_wave = first_wave; pc.wave2 = wave2;
+    hpv_partition(p, n_el, pts_per_el, tile_pts, max_ctas, 0, &pc);
+    *tiles_per_el = p.tiles_per_el;
+    for (int c = 0; c <= p.n_ctas; ++c) cta_tile_begin[c] = p.cta_tile_begin[c];
+    return p.n_ctas;
+}
+
 // padded parameter index -> compact gradient index of the reverse sweep (or -1), and the compact length
 int hpv_emu_gw_of_padded(int dim, int hp, int nhid, int ip) { return hpv_gw_of_padded(dim, hp, nhid, ip); }
 int hpv_emu_gw_n(int dim, int hp, int nhid) { return hpv_gw_n(dim, hp, nhid); }

@@ -43,6 +43,53 @@ def test_forward_partition_invariants(n_el, pts, tile, max_ctas, full):
     assert total == acc
 
 
+def _cost(tb, tpe, cross, first_wave, wave2):
+    out = []
+    for c in range(len(tb) - 1):
+        alpha = wave2 if (first_wave > 0 and c >= first_wave) else 1.0
+        inside = sum(1 for t in range(tb[c] + 1, tb[c + 1]) if t % tpe == 0)
+        out.append(alpha * (tb[c + 1] - tb[c]) + cross * inside)
+    return np.array(out)
+
+
+@settings(max_examples=100, deadline=None)
+@given(n_el=st.integers(1, 70), pts=st.integers(100, 7000), max_ctas=st.integers(2, 300), cross=st.floats(0.0, 3.0),
+       wave2=st.floats(1.0, 1.3))
+def test_weighted_forward_partition_covers_and_does_not_increase_the_modelled_maximum(n_el, pts, max_ctas, cross, wave2):
+    L = E.lib()
+    tile = 128
+    tb = np.zeros(max_ctas + 2, dtype=np.int32); tpe = ctypes.c_int(0)
+    ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+    L.hpv_emu_partition_weighted.argtypes = [ctypes.c_int] * 4 + [ctypes.c_double, ctypes.c_int, ctypes.c_double,
+                                                                   ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+    first_wave = max_ctas // 2
+    n = L.hpv_emu_partition_weighted(n_el, pts, tile, max_ctas, cross, first_wave, wave2, ctypes.byref(tpe), ip(tb))
+    tb = tb[:n + 1]; tpe = tpe.value
+    ntiles = n_el * tpe
+    assert tb[0] == 0 and tb[-1] == ntiles and np.all(np.diff(tb) >= (1 if ntiles >= n else 0))      # contiguous cover, nobody idle
+    # against equal tile counts the largest modelled cost does not grow
+    uniform = np.array([(ntiles * c) // n for c in range(n + 1)])
+    # (the assignment rounds every CTA to the cost nearest the running target: allow one rounding step)
+    assert _cost(tb, tpe, cross, first_wave, wave2).max() <= _cost(uniform, tpe, cross, first_wave, wave2).max() + wave2 + cross + 1e-6
+
+
+def test_weighted_partition_of_the_headline_case_relieves_the_ctas_that_straddle_elements():
+    L = E.lib()
+    tb = np.zeros(298, dtype=np.int32); tpe = ctypes.c_int(0)
+    ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+    L.hpv_emu_partition_weighted.argtypes = [ctypes.c_int] * 4 + [ctypes.c_double, ctypes.c_int, ctypes.c_double,
+                                                                   ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+    n = L.hpv_emu_partition_weighted(64, 6400, 128, 296, 2.4, 148, 1.16, ctypes.byref(tpe), ip(tb))     # C3 on 148 SMs x 2
+    assert n == 296 and tpe.value == 50
+    tb = tb[:n + 1]
+    cost = _cost(tb, 50, 2.4, 148, 1.16)
+    uniform = np.array([(3200 * c) // n for c in range(n + 1)])
+    assert cost.max() < _cost(uniform, 50, 2.4, 148, 1.16).max() - 1.0          # 15.2 -> about 12.6 tile times
+    assert cost.min() > cost.max() - 3.5                                      # nobody idles at the end of the list
+    sizes = np.diff(tb)
+    assert sizes[:148].mean() > sizes[148:].mean()                            # the second CTA of an SM gets less
+
+
 @pytest.mark.parametrize("dim", [1, 2])
 @pytest.mark.parametrize("hp", [8, 20, 32])
 @pytest.mark.parametrize("nhid", [1, 2, 3, 8])

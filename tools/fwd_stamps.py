@@ -33,4 +33,6 @@ for ne in (2, 8, 11, 16):
     print("     element publish / finish  ", rng(s[:, 8]))
     print("   exit (dealloc)              ", rng(s[:, 4] - s[:, 3]))
     print("   CTA end after first start   ", rng(s[:, 4] - t0), flush=True)
+    if ne == 8:
+        np.savetxt(os.path.join(os.environ.get('HPV_STAMP_OUT', '.'), 'fwd_stamps_c3_per_cta.csv'), s - t0 * (np.arange(NST) < 5), fmt='%.2f', delimiter=',')
     eng.close()
