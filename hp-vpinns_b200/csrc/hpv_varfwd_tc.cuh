@@ -568,15 +568,19 @@ __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVar
                     const int k = 4 * kt + i, r = 4 * rt + j;
                     Fv[i][j] = (a.F && k < nty_e && r < ntx_e) ? a.F[((size_t)e * a.nty + k) * a.ntx + r] : 0.0f;
                 }
-            hpv_fence();
+            // release / acquire through thread 0: the barrier orders every thread's stores of the part before thread 0's
+            // fence + counter increment, and thread 0's fence after a last arrival before every thread's loads of the
+            // other parts (one device-scope fence per CTA instead of one per thread)
             hpv_sync(c);
             if (tid == 0) {
+                hpv_fence();
                 unsigned int prev = hpv_atomic_inc(a.el_done + e);
-                s_flag[0] = (prev == (unsigned int)(nparts - 1)) ? 1 : 0;
+                const int last = (prev == (unsigned int)(nparts - 1)) ? 1 : 0;
+                if (last) hpv_fence();
+                s_flag[0] = last;
             }
             hpv_sync(c);
             if (s_flag[0]) {
-                hpv_fence();
                 float S[4][4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
