@@ -205,3 +205,37 @@ def test_sin_network_in_two_dimensions_and_tanh_in_one():
         assert np.allclose(d1, d1o.numpy(), rtol=1e-4, atol=1e-5)
         assert np.abs(d2 - d2o.numpy()).max() <= 1e-5 * max(1.0, np.abs(d2o.numpy()).max())
         eng.close()
+
+
+@pytest.mark.parametrize("name", ["p2d_vf1", "p1d_vf1", "adi_vf1"])
+def test_loss_total_of_a_step_equals_the_forward_kernels_own_total(name):
+    """In a step (hpv_loss_and_grad) the forward kernel leaves the sum of the element losses to the loss assembly of the
+    gradient reduction (defer_total); the stand-alone forward call forms it in its very last CTA.  Same element losses,
+    both summed in float64: the two totals agree to float rounding, and both match the fixture."""
+    c = C.load(name)
+    eng = G.make_engine(C.engine_inputs(c))
+    lossv, el = eng.varloss_forward(want_residual=False, want_el_loss=True)
+    eng.configure_training(wv=1.0, point_slots=(), train_eps=(c["kind"] == "advdiff"))
+    eng.loss_and_grad()
+    losses = eng.read_losses()
+    assert losses[1] == pytest.approx(np.float32(el.sum()), rel=2e-7)
+    assert losses[1] == pytest.approx(lossv, rel=2e-7)
+    assert lossv == pytest.approx(float(c["lossv"]), rel=1e-5)
+    eng.close()
+
+
+def test_forward_partition_weighting_does_not_change_the_result(monkeypatch):
+    """The tensor-core forward kernel distributes its tiles over the CTAs by a cost model (HPV_FWD_BALANCE, read when
+    the launch plan is made); with equal tile counts the partial sums of an element are formed over different point
+    ranges, so the residuals may differ in the last bits -- and by no more."""
+    c = C.load("p2d_vf1_w20")
+    inp = C.engine_inputs(c)
+    got = {}
+    for b in ("0", "1"):
+        monkeypatch.setenv("HPV_FWD_BALANCE", b)
+        eng = G.make_engine(inp)
+        got[b] = eng.varloss_forward(want_residual=True)
+        eng.close()
+    assert got["0"][0] == pytest.approx(got["1"][0], rel=1e-6)
+    assert np.abs(got["0"][1] - got["1"][1]).max() <= 2e-6 * np.abs(got["1"][1]).max()
+    assert got["1"][0] == pytest.approx(float(c["lossv"]), rel=1e-5)
