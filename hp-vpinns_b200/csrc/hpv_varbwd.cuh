@@ -136,7 +136,7 @@ HPV_HD void hpv_adjproj_body(const HpvCta& c, const HpvAdjArgs& aa) {
             }
         }
     }
-    hpv_pdl_trigger();       // at the end, see hpv_varfwd_body
+    hpv_pdl_trigger();       // at the end, see hpv_varfwd_body (triggering at the start was measured: no gain, r2z2)
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -344,6 +344,12 @@ __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVar
         hpv_tmem_wait_st();
     }
     HPV_STAMP(1);
+    // Programmatic dependent launch: from here on the next kernel of the step (adjoint projection) may be scheduled.  The
+    // grid of this kernel is persistent and fully resident, so nothing of it can be displaced (the reason the FFMA form
+    // triggers at its end); CTAs of the dependent kernel move into the SMs as CTAs of this grid exit -- the slowest CTA
+    // ends 6 us after the median one -- and stage their tables before they wait for this grid to complete
+    // (C3 step 214.9 -> 212.1 us, profiles/round2_tuning/pdl_trigger_early.txt).
+    hpv_pdl_trigger();
     hpv_mbar_wait(&s_bar[HPV_NFIELDS], 0);      // tables have landed
     HPV_STAMP(2);
 
@@ -646,7 +652,6 @@ __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVar
         HPV_STAMP_ADD(8, ts_fin);
     }
     HPV_STAMP(3);
-    hpv_pdl_trigger();
     hpv_tc_fence_before();
     __syncthreads();
     if (warp == 0) hpv_tmem_dealloc(tb, TCOLS);
