@@ -496,7 +496,7 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
     }
 #undef HPV_P
 
-    hpv_pdl_trigger();       // the sweep of this CTA is done (at the end, see hpv_varfwd_body)
+    hpv_pdl_trigger();       // the sweep of this CTA is done (at the end, see hpv_varfwd_body; at the start: no gain, r2z3)
     // ---- publish this CTA's partial gradient: the warps' accumulators summed in a fixed order, padded layout ----
     const float dtot = hpv_block_sum(c, s_red, deps);
     float* gpart = a.grad_part + (size_t)c.bid * a.grad_stride;
