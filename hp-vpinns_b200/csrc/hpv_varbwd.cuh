@@ -297,6 +297,23 @@ HPV_HD void hpv_wgrad_warp(const HpvCta& c, const float* IN, const float* ADJ, f
     }
 }
 
+#if defined(HPV_EXP_STAMPS) && defined(__CUDACC__)
+// Timing experiment only (tools/bwd_stamps.py): %globaltimer of every CTA at entry [0], after the wait for the previous
+// kernel [1], at the end of each warp's sweep [2 + warp] and at the CTA's end [20]; hpv_exp_read_bstamps (hpv_k_h20_bwd.cu).
+#define HPV_EXP_NBSTAMP 24
+static __device__ unsigned long long hpv_exp_bstamps[256 * HPV_EXP_NBSTAMP];
+__device__ __forceinline__ void hpv_exp_bstamp(int bid, int slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (bid < 256) hpv_exp_bstamps[bid * HPV_EXP_NBSTAMP + slot] = t;
+}
+#endif
+#if defined(HPV_EXP_STAMPS) && defined(__CUDA_ARCH__)
+#define HPV_BSTAMP(cond, slot) do { if (cond) hpv_exp_bstamp(c.bid, (slot)); } while (0)
+#else
+#define HPV_BSTAMP(cond, slot) do { } while (0)
+#endif
+
 // The reverse sweep.  A warp takes a contiguous range of 32-point tiles and runs, per tile and without waiting
 // for any other warp: forward recompute (pre-activations kept in the slots), output-layer gradient, then per
 // hidden layer top-down the activation adjoint, the weight-gradient GEMM over the warp's points and the
@@ -335,9 +352,11 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
     static_assert(NCH1 * 4 <= M::NCH * SP, "the layer-1 input rows must fit into a slot");
 #define HPV_P(l) (slots_w + (size_t)((l) - 1) * L.slot_sz)
 
+    HPV_BSTAMP(tid == 0, 0);
     for (int i = lane; i < L.gwn; i += 32) s_gw[i] = 0.0f;
     if (tid < 8) s_cst[tid] = (tid == 0) ? 1.0f : 0.0f;
     hpv_pdl_wait();                                      // Gbar (or the point adjoints) of the previous kernel
+    HPV_BSTAMP(tid == 0, 1);
     const float eps = a.eps[0];
     float coef[HPV_MAX_TERMS][HPV_NFIELDS], coef1[HPV_MAX_TERMS][HPV_NFIELDS];      // registers: every loop over them is unrolled
 #pragma unroll
@@ -496,6 +515,7 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
     }
 #undef HPV_P
 
+    HPV_BSTAMP(lane == 0 && warp < 18, 2 + warp);
     hpv_pdl_trigger();       // the sweep of this CTA is done (at the end, see hpv_varfwd_body; at the start: no gain, r2z3)
     // ---- publish this CTA's partial gradient: the warps' accumulators summed in a fixed order, padded layout ----
     const float dtot = hpv_block_sum(c, s_red, deps);
@@ -509,6 +529,7 @@ HPV_HD void hpv_mlpbwd_body(const HpvCta& c, const HpvBwdArgs& ba) {
         gpart[ip] = sum;
     }
     if (tid == 0) gpart[a.theta_pad_n] = dtot;
+    HPV_BSTAMP(tid == 0, 20);
 }
 
 // K3: grad_pad[i] (+)= sum over CTAs of grad_part[c][i], fixed order.  One CTA = 32 entries x (nthreads / 32)
