@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- element-residuals/sec of the hp-VPINN variational-loss path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload auto|c2|c3|c4|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload auto|c1|c2|c3|c4|c5]
 
 A "step" is one full pass of the hot path over the element batch: fused forward (element residuals + lossv),
 backward (d lossv / d theta), [N>1: sum of loss + gradient over the GPUs], TF1-Adam update -- what one
@@ -10,7 +10,8 @@ backward (d lossv / d theta), [N>1: sum of loss + gradient over the GPUs], TF1-A
 Workloads (BASELINE.json configs): c3 = 2-D Poisson 8x8 elements, Q=80x80, 60x60 test functions, MLP [2,20,20,20,1]
 (the configuration the metric is quoted on; default at N=1); c4 = 32x32 elements of the same, block-partitioned
 over the ranks (default at N>1: strong scaling, total work fixed -- the N=1 line carries the C4 single-GPU step as
-`strong_scaling_base`); c2 = 1-D Poisson, 16 elements, Q=80, 60 test functions, [1,20,20,20,1]; c5 = AdvDiff
+`strong_scaling_base`); c2 = 1-D Poisson, 16 elements, Q=80, 60 test functions, [1,20,20,20,1]; c1 = 1-D Poisson, 4 elements, Q=50, 5 test
+functions, [1,5,5,1] (the reference's own CPU-sized case); c5 = AdvDiff
 identification, 20 elements, Q=80x80, 60x60 test functions, [2,20,20,20,1] + eps.
 
 Timed on the device with CUDA events around every step (L2 flushed by an untimed 256 MB fill between steps),
@@ -65,6 +66,8 @@ def xavier_theta(layers, seed=1234):
 
 
 WORKLOADS = {
+    "c1": dict(kind="poisson1d", ne=4, Q=50, N=5, layers=[1, 5, 5, 1], act="sin", vf=1, nch=3, n_terms=1,
+               desc="C1: 1-D Poisson, 4 elements, Q=50, N_test=5, MLP [1,5,5,1], var_form 1 (the reference's own CPU-sized case)"),
     "c2": dict(kind="poisson1d", ne=16, Q=80, N=60, layers=[1, 20, 20, 20, 1], act="sin", vf=1, nch=3, n_terms=1,
                desc="C2: 1-D Poisson, 16 elements, Q=80, N_test=60, MLP [1,20,20,20,1], var_form 1"),
     "c3": dict(kind="poisson2d", ne=8, Q=80, N=60, layers=[2, 20, 20, 20, 1], act="tanh", vf=1, nch=3, n_terms=2,
@@ -324,7 +327,7 @@ def cpu_baseline(wl, budget_s=18.0):
             torch.autograd.grad(loss, Wt + bt, allow_unused=True)
             done += wl["n_el_local"]; reps += 1
         el = time.perf_counter() - t0
-        sample = "%d passes over the %d elements of C2, literal forward + backward (incl. the per-element table evaluation)" % (reps, wl["n_el_local"])
+        sample = "%d passes over the %d elements of %s, literal forward + backward (incl. the per-element table evaluation)" % (reps, wl["n_el_local"], wl["name"].upper())
     else:
         X, WX, XT, WXT = O.tensor_quadrature(wl["Q"])
         XT = XT.copy(); XT[:, 1] = XT[:, 1]                               # reference coordinates; the element map is applied inside
@@ -641,7 +644,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scaling-base", action="store_true", help="N=1: skip the C4 single-GPU step (strong_scaling_base)")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
