@@ -508,15 +508,34 @@ __device__ __forceinline__ void hpv_varfwd_tc_body(const HpvCta& c, const HpvVar
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+                if ((Q & 3) == 0) {
+                    // four quadrature nodes per trip: the field rows come in as 128-bit loads (rows start at multiples of
+                    // Q floats) -- 8 shared-memory loads per 64 FMAs instead of 20; same summation order as below
+#pragma unroll 2
+                    for (int i = 0; i < Q; i += 4) {
+                        const HpvF4 a0 = hpv_ld4(g0 + i), a1 = hpv_ld4(g1 + i), a2 = hpv_ld4(g2 + i), a3 = hpv_ld4(g3 + i);
+                        const float gq[4][4] = {{a0.x, a1.x, a2.x, a3.x}, {a0.y, a1.y, a2.y, a3.y}, {a0.z, a1.z, a2.z, a3.z}, {a0.w, a1.w, a2.w, a3.w}};
+#pragma unroll
+                        for (int ii = 0; ii < 4; ++ii) {
+                            const HpvF4 w = hpv_ld4(R + (i + ii) * HPV_NP);
+                            const float ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                                for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(gq[ii][u], ws[v], acc[u][v]);
+                        }
+                    }
+                } else {
 #pragma unroll 4
-                for (int i = 0; i < Q; ++i) {
-                    const HpvF4 w = hpv_ld4(R + i * HPV_NP);
-                    const float gv[4] = {g0[i], g1[i], g2[i], g3[i]};
-                    const float ws[4] = {w.x, w.y, w.z, w.w};
+                    for (int i = 0; i < Q; ++i) {
+                        const HpvF4 w = hpv_ld4(R + i * HPV_NP);
+                        const float gv[4] = {g0[i], g1[i], g2[i], g3[i]};
+                        const float ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
+                        for (int u = 0; u < 4; ++u)
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(gv[u], ws[v], acc[u][v]);
+                            for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(gv[u], ws[v], acc[u][v]);
+                    }
                 }
                 const float ct = hpv_term_scale(a.terms[t], hwx, hwy);
 #pragma unroll
