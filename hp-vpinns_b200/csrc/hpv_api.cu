@@ -360,6 +360,8 @@ int ensure_ready(hpv_ctx* c) {
             const double avg = (double)ntiles / (double)(c->n_sm * c->fwd_ctas_per_sm);
             pc.cross = avg >= 8.0 ? 2.4 : 0.3 * avg;
             if (c->fwd_ctas_per_sm == 2) { pc.first_wave = c->n_sm; pc.wave2 = 1.16; }
+            if (const char* e1 = getenv("HPV_FWD_BALANCE_CROSS")) pc.cross = atof(e1);          // tuning overrides
+            if (const char* e2 = getenv("HPV_FWD_BALANCE_WAVE2")) { if (c->fwd_ctas_per_sm == 2) pc.wave2 = atof(e2); }
         }
         hpv_partition(c->part, c->n_el, rows * c->Q, c->part_tile, c->n_sm * c->fwd_ctas_per_sm, c->fwd_tc_active ? 0 : HPV_THREADS, &pc);
     }
