@@ -59,11 +59,25 @@ HPV_HD void hpv_adjproj_body(const HpvCta& c, const HpvAdjArgs& aa) {
     hpv_pdl_wait();                                      // Res of the forward kernel from here on
     const int ntx_e = a.el_ntest[2 * e + 0], nty_e = a.el_ntest[2 * e + 1];
     const float rs = a.loss_scale * 2.0f / (float)(ntx_e * nty_e);
-    for (int idx = tid; idx < HPV_NP * HPV_NP; idx += T) {
-        const int k = idx >> 6, r = idx & 63;
-        float v = 0.0f;
-        if (k < nty_e && r < ntx_e) v = rs * a.Res[((size_t)e * a.nty + k) * a.ntx + r];
-        s_R[idx] = v;
+    constexpr int RPT = HPV_NP * HPV_NP / HPV_THREADS;       // entries per thread of a full-size CTA
+    if (T == HPV_THREADS) {
+        // every load of the residual in flight before the first use: this sits right behind the wait for the forward
+        // kernel, on the step's critical path (four dependent rounds of four loads before)
+        float rv[RPT];
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) {
+            const int idx = tid + q * HPV_THREADS, k = idx >> 6, r = idx & 63;
+            rv[q] = (k < nty_e && r < ntx_e) ? a.Res[((size_t)e * a.nty + k) * a.ntx + r] : 0.0f;
+        }
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) s_R[tid + q * HPV_THREADS] = rs * rv[q];
+    } else {
+        for (int idx = tid; idx < HPV_NP * HPV_NP; idx += T) {
+            const int k = idx >> 6, r = idx & 63;
+            float v = 0.0f;
+            if (k < nty_e && r < ntx_e) v = rs * a.Res[((size_t)e * a.nty + k) * a.ntx + r];
+            s_R[idx] = v;
+        }
     }
     hpv_sync(c);
 
@@ -128,6 +142,11 @@ HPV_HD void hpv_adjproj_body(const HpvCta& c, const HpvAdjArgs& aa) {
             for (int i = 0; i < 4; ++i) {
                 const int jl = 4 * jl4 + i;
                 if (jl >= nrows) continue;
+                if ((Q & 3) == 0 && 4 * i4 + 3 < Q) {             // rows start at multiples of four floats: one 128-bit store
+                    HpvF4 o; o.x = ct * acc[i][0]; o.y = ct * acc[i][1]; o.z = ct * acc[i][2]; o.w = ct * acc[i][3];
+                    hpv_st4(out + (j0 + jl) * Q + 4 * i4, o);
+                    continue;
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int ii = 4 * i4 + j;
